@@ -1,0 +1,171 @@
+/* pydisort_b200.h -- C ABI of libpydisort_b200.so (sm_100a CUDA kernels).
+ *
+ * Drop-in boundary for the PythonicDISORT solver hot path.  The reference has
+ * no FFI: its seam is the Python function PythonicDISORT.pydisort
+ * (src/PythonicDISORT/pydisort.py:13-29) and, below it, the private
+ * _assemble_intensity_and_fluxes (src/PythonicDISORT/_assemble_intensity_and_fluxes.py:8-32).
+ * Each entry point below names the reference code it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to FP64 (or int32 where said) owned by
+ *    the caller; the library never allocates, frees or keeps state;
+ *  - arrays are C-contiguous with the shapes given, B (columns) outermost;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *  - return value: 0 ok, <0 invalid argument, >0 cudaError_t of the launch.
+ *    Numerical trouble (QR non-convergence, non-positive k^2, zero pivot) is
+ *    reported per column in the `status` array (bit mask PD_ST_*), not thrown.
+ *  - N = NQuad/2; stream order of every "2N" axis is [+mu_1..+mu_N, -mu_1..-mu_N]
+ *    (pydisort.py:304-305).
+ */
+#ifndef PYDISORT_B200_H
+#define PYDISORT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PD_ABI_VERSION 1
+
+/* pd_config.flags */
+#define PD_FLAG_BEAM      (1 << 0) /* there_is_beam_source  (pydisort.py:215)            */
+#define PD_FLAG_ISO       (1 << 1) /* there_is_iso_source   (pydisort.py:216)            */
+#define PD_FLAG_DELTA_M   (1 << 2) /* np.any(f_arr > 0)     (pydisort.py:316)            */
+#define PD_FLAG_BDRF_PERCOL (1 << 3) /* bdrf_q / bdrf_q0 carry a leading B axis          */
+
+/* per-column status bits (pd_solve) */
+#define PD_ST_QR_NOCONV   (1 << 0) /* shifted QR hit its iteration cap                   */
+#define PD_ST_BAD_EIGEN   (1 << 1) /* k^2 <= 0 or non-finite: reference would give NaN   */
+#define PD_ST_ZERO_PIVOT  (1 << 2) /* exactly singular pivot in an LU                    */
+
+/* input-check bits (pd_prologue), one per ValueError of pydisort.py:223-288 */
+#define PD_CHK_TAU_POS      (1 << 0)  /* :223 tau values cannot be non-positive          */
+#define PD_CHK_THICK_POS    (1 << 1)  /* :225 layer thicknesses cannot be non-positive   */
+#define PD_CHK_OMEGA_RANGE  (1 << 2)  /* :228 omega must be in [0, 1)                    */
+#define PD_CHK_LEG_RANGE    (1 << 3)  /* :249 Legendre coefficients must be in (-1, 1)   */
+#define PD_CHK_I0_NEG       (1 << 4)  /* :266 beam intensity cannot be negative          */
+#define PD_CHK_MU0_RANGE    (1 << 5)  /* :269 mu0 must be in (0, 1]                      */
+#define PD_CHK_PHI0_RANGE   (1 << 6)  /* :271 phi0 must be in [0, 2 pi)                  */
+#define PD_CHK_F_RANGE      (1 << 7)  /* :287 f must be in [0, 1]                        */
+#define PD_CHK_LEG0_FIXED   (1 << 8)  /* :246 warning: g_0 != 1 was corrected            */
+#define PD_CHK_OMEGA_NEAR1  (1 << 9)  /* :340 warning: scaled omega > 1 - 1e-6           */
+#define PD_CHK_LEG_NEAR1    (1 << 10) /* :342 warning: |scaled g_l| > 0.95               */
+#define PD_CHK_MU0_AT_NODE  (1 << 11) /* :309 NT_cor and |mu_i - mu0| < 1e-8             */
+
+typedef struct pd_config {
+    int32_t B;         /* columns in this call                                             */
+    int32_t L;         /* NLayers                                                          */
+    int32_t NQuad;     /* streams, even, >= 2                                              */
+    int32_t NLeg;      /* Legendre terms used by the solver, NFourier <= NLeg <= NQuad     */
+    int32_t NLeg_all;  /* Legendre terms supplied (>= NLeg; the NT corrections use all)    */
+    int32_t NFourier;  /* azimuthal modes solved                                           */
+    int32_t NBDRF;     /* BDRF Fourier modes supplied (0 = black surface)                  */
+    int32_t Nscoeffs;  /* thermal source polynomial coefficients per layer (0 = none)      */
+    int32_t NFb;       /* leading size of b_pos / b_neg mode axis: 1 (mode 0 only) or NFourier */
+    int32_t flags;     /* PD_FLAG_*                                                        */
+} pd_config;
+
+int pd_abi_version(void);
+
+/* Scratch needed by pd_solve for this configuration (bytes, device memory).
+ * The boundary-condition kernel keeps one LU panel history per resident warp. */
+size_t pd_workspace_bytes(const pd_config* cfg);
+
+/* pydisort prologue: input checks, delta-M scaling, thermal-source rescaling
+ * and affine transform, source rescale (pydisort.py:223-372), plus the
+ * normalised associated Legendre functions at -mu0 for every column
+ * (_solve_for_gen_and_part_sols.py:80,101-103).
+ *
+ * in : tau[B][L] omega[B][L] leg_all[B][L][NLeg_all] f[B][L] s_poly[B][L][Ns]
+ *      mu0[B] I0[B] phi0[B] b_pos[B][NFb][N] b_neg[B][NFb][N]   (f, s_poly may be NULL)
+ *      mu_nodes[N] (for the NT mu0-vs-node check; pass nt_requested != 0)
+ * out: taus[B][L+1] omega_s[B][L] wleg[B][L][NLeg] scale_tau[B][L] s_s[B][L][Ns]
+ *      colp[B][PD_NCOLP] (PD_COL_* below) bpos_s[B][NFb][N] bneg_s[B][NFb][N]
+ *      pmu0[B][NFourier][NLeg]  checks[1] (OR of PD_CHK_* over all columns, int32) */
+#define PD_NCOLP 8
+#define PD_COL_MU0     0
+#define PD_COL_I0      1  /* rescaled beam intensity                          */
+#define PD_COL_RESCALE 2  /* rescale_factor (pydisort.py:351-370)             */
+#define PD_COL_PHI0    3
+#define PD_COL_I0_RAW  4
+#define PD_COL_DM      5  /* 1.0 if this column is delta-M scaled (any f > 0), else 0.0 */
+#define PD_COL_NT      6  /* 1.0 if the column-dependent part of the NT gate holds (pydisort.py:375) */
+int pd_prologue(const pd_config* cfg,
+                const double* tau, const double* omega, const double* leg_all, const double* f,
+                const double* s_poly, const double* mu0, const double* I0, const double* phi0,
+                const double* b_pos, const double* b_neg, const double* mu_nodes, int nt_requested,
+                double* taus, double* omega_s, double* wleg, double* scale_tau, double* s_s,
+                double* colp, double* bpos_s, double* bneg_s, double* pmu0, int32_t* checks,
+                void* stream);
+
+/* The solve: replaces _solve_for_gen_and_part_sols (whole file) and
+ * _solve_for_coeffs (whole file) as orchestrated by
+ * _assemble_intensity_and_fluxes.py:109-164.
+ *
+ * in : prologue outputs; mu_nodes[N] w_nodes[N];
+ *      ptab[NFourier][NLeg][N]  normalised P~_l^m(mu_i), zero for l < m;
+ *      bdrf_q[(B)][NBDRF][N][N] q^m(mu_i, mu_j); bdrf_q0[(B)][NBDRF][N] q^m(mu_i, mu0)
+ * out: K  [B][NFourier][L][N]      positive eigenvalues k (K_collect = [-k, +k])
+ *      G  [B][NFourier][L][2][N][N] the two distinct blocks of G_collect:
+ *                                   G[0] = G[:N,:N] = G[N:,N:],  G[1] = G[:N,N:] = G[N:,:N]
+ *      Bv [B][NFourier][L][2N]     beam particular solution (B_collect)
+ *      dth[B][L][Ns][2N]           thermal particular solution, coefficient of tau*^q
+ *      C  [B][NFourier][L][2N]     boundary-condition coefficients (GC_collect = G * C)
+ *      status[B] int32             PD_ST_* bits */
+int pd_solve(const pd_config* cfg,
+             const double* taus, const double* omega_s, const double* wleg, const double* s_s,
+             const double* colp, const double* bpos_s, const double* bneg_s, const double* pmu0,
+             const double* mu_nodes, const double* w_nodes, const double* ptab,
+             const double* bdrf_q, const double* bdrf_q0,
+             void* workspace, size_t workspace_bytes,
+             double* K, double* G, double* Bv, double* dth, double* C, int32_t* status,
+             void* stream);
+
+/* Output functions evaluated at ntau optical depths per column
+ * (tau_q[B][ntau], unscaled tau as the user gives it; each value must lie in
+ * [0, tau_L], checked by the caller).  `anti` != 0 selects the tau-antiderivative.
+ *
+ * pd_eval_flux : flux_up / flux_down, _assemble_intensity_and_fluxes.py:446-613
+ *   out Fup[B][ntau] Fdn_diffuse[B][ntau] Fdn_direct[B][ntau]
+ * pd_eval_u0   : u0 (+ actinic reclassification term), :334-433
+ *   out u0[B][2N][ntau]  recl[B][ntau] (may be NULL)
+ * pd_eval_u    : u, :170-329, summed over modes at nphi azimuths phi_q[nphi]
+ *   out u[B][2N][ntau][nphi]; if nt != 0 the Nakajima-Tanaka TMS + IMS
+ *   corrections (pydisort.py:409-694) are added (needs leg_all, f, omega, tau);
+ *   ulast[B][2N][ntau] (may be NULL) receives the last Fourier mode for the
+ *   Cauchy convergence estimate (:265-316). */
+typedef struct pd_state {
+    const double* tau;       /* [B][L]   unscaled layer bottoms                    */
+    const double* taus;      /* [B][L+1]                                            */
+    const double* scale_tau; /* [B][L]                                              */
+    const double* colp;      /* [B][PD_NCOLP]                                       */
+    const double* K;
+    const double* G;
+    const double* Bv;
+    const double* dth;
+    const double* C;
+    const double* mu_nodes;
+    const double* w_nodes;
+} pd_state;
+
+int pd_eval_flux(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau, int anti,
+                 double* Fup, double* Fdn_diffuse, double* Fdn_direct, void* stream);
+int pd_eval_u0(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau, int anti,
+               double* u0, double* recl, void* stream);
+int pd_eval_u(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau,
+              const double* phi_q, int nphi, int anti, int nt,
+              const double* omega, const double* f, const double* leg_all,
+              const double* omega_s, const double* wleg,
+              double* u, double* ulast, void* stream);
+
+/* FP64 FMA throughput probe (one launch of dependent-free DFMA chains); used
+ * by bench.py to measure the FP64 roofline denominator on the box.
+ * Returns the number of FLOPs the launch performs; time it with CUDA events. */
+double pd_fp64_probe(double* sink, int iters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYDISORT_B200_H */

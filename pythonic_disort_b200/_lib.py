@@ -1,0 +1,98 @@
+"""ctypes binding of libpydisort_b200.so (C ABI: include/pydisort_b200.h) and
+the in-tree build recipe (nvcc, sm_100a only)."""
+import ctypes
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libpydisort_b200.so")
+SOURCES = ["pd_kernels.cu"]
+HEADERS = ["pd_common.cuh", "pd_linalg.cuh", "pd_stage_a.cuh", "pd_stage_b.cuh", "pd_eval.cuh", "pd_prologue.cuh",
+           os.path.join("..", "..", "include", "pydisort_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class pd_config(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("B", "L", "NQuad", "NLeg", "NLeg_all", "NFourier", "NBDRF", "Nscoeffs", "NFb", "flags")]
+
+
+class pd_state(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ("tau", "taus", "scale_tau", "colp", "K", "G", "Bv", "dth", "C", "mu_nodes", "w_nodes")]
+
+
+# constants of include/pydisort_b200.h
+PD_FLAG_BEAM, PD_FLAG_ISO, PD_FLAG_DELTA_M, PD_FLAG_BDRF_PERCOL = 1, 2, 4, 8
+PD_ST_QR_NOCONV, PD_ST_BAD_EIGEN, PD_ST_ZERO_PIVOT = 1, 2, 4
+PD_NCOLP = 8
+PD_COL_MU0, PD_COL_I0, PD_COL_RESCALE, PD_COL_PHI0, PD_COL_I0_RAW, PD_COL_DM, PD_COL_NT = 0, 1, 2, 3, 4, 5, 6
+CHK = dict(TAU_POS=1 << 0, THICK_POS=1 << 1, OMEGA_RANGE=1 << 2, LEG_RANGE=1 << 3, I0_NEG=1 << 4, MU0_RANGE=1 << 5,
+           PHI0_RANGE=1 << 6, F_RANGE=1 << 7, LEG0_FIXED=1 << 8, OMEGA_NEAR1=1 << 9, LEG_NEAR1=1 << 10,
+           MU0_AT_NODE=1 << 11)
+
+EXPORTS = ["pd_abi_version", "pd_workspace_bytes", "pd_prologue", "pd_solve", "pd_eval_flux", "pd_eval_u0",
+           "pd_eval_u", "pd_fp64_probe"]
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def bind(path):
+    """Load a library exporting the C ABI and declare argument types."""
+    lib = ctypes.CDLL(path)
+    vp, ci, cfgp, stp = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(pd_config), ctypes.POINTER(pd_state)
+    lib.pd_abi_version.restype = ci
+    lib.pd_workspace_bytes.restype = ctypes.c_size_t
+    lib.pd_workspace_bytes.argtypes = [cfgp]
+    lib.pd_prologue.restype = ci
+    lib.pd_prologue.argtypes = [cfgp] + [vp] * 11 + [ci] + [vp] * 10 + [vp]
+    lib.pd_solve.restype = ci
+    lib.pd_solve.argtypes = [cfgp] + [vp] * 13 + [vp, ctypes.c_size_t] + [vp] * 6 + [vp]
+    lib.pd_eval_flux.restype = ci
+    lib.pd_eval_flux.argtypes = [cfgp, stp, vp, ci, ci, vp, vp, vp, vp]
+    lib.pd_eval_u0.restype = ci
+    lib.pd_eval_u0.argtypes = [cfgp, stp, vp, ci, ci, vp, vp, vp]
+    lib.pd_eval_u.restype = ci
+    lib.pd_eval_u.argtypes = [cfgp, stp, vp, ci, vp, ci, ci, ci] + [vp] * 5 + [vp, vp, vp]
+    lib.pd_fp64_probe.restype = ctypes.c_double
+    lib.pd_fp64_probe.argtypes = [vp, ci, vp]
+    if lib.pd_abi_version() != 1:
+        raise RuntimeError("libpydisort_b200 ABI mismatch")
+    return lib
+
+
+_cuda_lib = None
+
+
+def cuda_lib():
+    """The CUDA library; there is no other implementation to fall back to."""
+    global _cuda_lib
+    if _cuda_lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(pythonic_disort_b200 has no CPU or PyTorch fallback)")
+        _cuda_lib = bind(LIB_PATH)
+    return _cuda_lib

@@ -1,0 +1,560 @@
+"""Host side of the drop-in boundary: ``pydisort`` with the reference's call
+signature (src/PythonicDISORT/pydisort.py:13-29) extended by a leading
+batch-of-columns dimension, returning the same output functions
+(src/PythonicDISORT/_assemble_intensity_and_fluxes.py:170-613).
+
+Everything numerical happens in libpydisort_b200.so (CUDA, sm_100a) through
+ctypes; PyTorch only owns device memory and the stream.  There is no CPU or
+PyTorch implementation to fall back to.
+
+Batch conventions (B = number of columns)
+  * ``tau_arr`` 2-D ``[B, NLayers]`` switches batch mode on; with a 0-D/1-D
+    ``tau_arr`` the call is the reference's single-column call and outputs are
+    squeezed exactly like the reference's.
+  * In batch mode every other array input may carry a leading ``B`` axis
+    (``omega_arr [B, L]``, ``Leg_coeffs_all [B, L, NLeg_all]``, ``f_arr [B, L]``,
+    ``s_poly_coeffs [B, L, Ns]``, ``mu0 / I0 / phi0 [B]``) or keep the reference's
+    unbatched shape, in which case it is shared by all columns.
+  * ``b_pos`` / ``b_neg`` per column: ``[B]`` or ``[B, 1]`` (isotropic), ``[B, N]``
+    or ``[B, N, NFourier]``.
+  * ``BDRF_Fourier_modes`` entries: a scalar, a callable ``f(mu, -mu_p)``, a
+    ``subroutines.TabulatedBDRF`` or (batch mode) an array ``[B]`` of per-column
+    Lambertian albedos.
+  * Output functions take ``tau`` as a scalar / 1-D array shared by all columns
+    or ``[B, ntau]``; results have shape ``[B, <reference shape>]``.
+  * NumPy in -> NumPy out; if any input is a CUDA tensor, outputs are CUDA tensors.
+"""
+import ctypes
+import warnings
+from math import pi
+
+import numpy as np
+import torch
+
+from . import _lib
+from .subroutines import Gauss_Legendre_quad, TabulatedBDRF
+
+_F64 = torch.float64
+_test_backend = None  # set by tests/hostsim only: (ctypes lib, torch.device("cpu"))
+_const_cache = {}
+
+
+def _backend():
+    if _test_backend is not None:
+        return _test_backend
+    if not torch.cuda.is_available():
+        raise RuntimeError("pythonic_disort_b200 needs a CUDA device (B200, sm_100a); it has no CPU fallback")
+    return _lib.cuda_lib(), torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream) if dev.type == "cuda" else None
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def norm_assoc_legendre_table(NF, NLeg, x):
+    """P~_l^m(x_i) = sqrt((l-m)!/(l+m)!) P_l^m(x_i) as ``[NF, NLeg, len(x)]``
+    (zero for l < m); same recurrence as csrc/pd_prologue.cuh."""
+    x = np.atleast_1d(np.asarray(x, dtype=float))
+    out = np.zeros((NF, NLeg, len(x)))
+    s = np.sqrt(np.maximum(0.0, 1.0 - x * x))
+    pmm = np.ones_like(x)
+    for m in range(NF):
+        if m > 0:
+            pmm = pmm * (-np.sqrt((2.0 * m - 1.0) / (2.0 * m)) * s)
+        if m >= NLeg:
+            break
+        out[m, m] = pmm
+        pm1, p = np.zeros_like(x), pmm
+        for l in range(m, NLeg - 1):
+            nxt = ((2.0 * l + 1.0) * x * p - np.sqrt(float((l + m) * (l - m))) * pm1) / np.sqrt(
+                float((l + 1 - m) * (l + 1 + m)))
+            out[m, l + 1] = nxt
+            pm1, p = p, nxt
+    return out
+
+
+def _constants(NQuad, NLeg, NF, dev):
+    key = (NQuad, NLeg, NF, str(dev))
+    if key not in _const_cache:
+        N = NQuad // 2
+        mu, W = Gauss_Legendre_quad(N)
+        ptab = norm_assoc_legendre_table(NF, NLeg, mu)
+        _const_cache[key] = (mu, W, torch.as_tensor(mu, dtype=_F64, device=dev),
+                             torch.as_tensor(W, dtype=_F64, device=dev),
+                             torch.as_tensor(ptab, dtype=_F64, device=dev).contiguous())
+    return _const_cache[key]
+
+
+def _is_dev_tensor(x):
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+class _Solution:
+    """Solved state of a batch of columns (device tensors) + evaluation launches."""
+
+    def __init__(self):
+        pass
+
+    # -- helpers -----------------------------------------------------------------
+    def _tau_points(self, tau):
+        t = torch.as_tensor(tau, dtype=_F64, device=self.dev) if not isinstance(tau, torch.Tensor) \
+            else tau.to(device=self.dev, dtype=_F64)
+        scalar = t.ndim == 0
+        if t.ndim == 0:
+            t = t[None]
+        if t.ndim == 1:
+            tq = t[None, :].expand(self.B, t.shape[0])
+        elif t.ndim == 2 and self.batched and t.shape[0] == self.B:
+            tq = t
+        else:
+            raise ValueError("tau must be a scalar, a 1-D array, or (batch mode) a [B, ntau] array.")
+        tq = tq.contiguous()
+        if bool(((tq < 0) | (tq > self.tau[:, -1:])).any()):
+            raise ValueError("tau input outside the tau range given for the atmosphere (check `tau_arr`).")
+        return tq, scalar
+
+    def _finish(self, out, ref_dims):
+        """Squeeze like the reference (``np.squeeze(x)[()]``) but never the batch axis."""
+        keep = [d for d in ref_dims if d != 1]
+        out = out.reshape([self.B] + keep)
+        if not self.batched:
+            out = out[0]
+        if self.want_torch:
+            return out
+        res = out.cpu().numpy()
+        return res[()] if res.ndim == 0 else res
+
+    def _state(self):
+        st = _lib.pd_state()
+        for name, t in (("tau", self.tau), ("taus", self.taus), ("scale_tau", self.scale_tau), ("colp", self.colp),
+                        ("K", self.K), ("G", self.G), ("Bv", self.Bv), ("dth", self.dth), ("C", self.C),
+                        ("mu_nodes", self.mu_d), ("w_nodes", self.w_d)):
+            setattr(st, name, t.data_ptr() if t is not None else None)
+        return st
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"libpydisort_b200: {what} failed with code {rc}")
+
+    # -- launches ----------------------------------------------------------------
+    def eval_flux(self, tau, anti):
+        tq, _ = self._tau_points(tau)
+        ntau = tq.shape[1]
+        out = torch.empty((3, self.B, ntau), dtype=_F64, device=self.dev)
+        st = self._state()
+        self._check(self.lib.pd_eval_flux(ctypes.byref(self.cfg), ctypes.byref(st), _ptr(tq), ntau, int(bool(anti)),
+                                          _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream(self.dev)), "pd_eval_flux")
+        return out, ntau
+
+    def eval_u0(self, tau, anti, want_recl):
+        tq, _ = self._tau_points(tau)
+        ntau = tq.shape[1]
+        u0 = torch.empty((self.B, self.NQuad, ntau), dtype=_F64, device=self.dev)
+        recl = torch.empty((self.B, ntau), dtype=_F64, device=self.dev) if want_recl else None
+        st = self._state()
+        self._check(self.lib.pd_eval_u0(ctypes.byref(self.cfg), ctypes.byref(st), _ptr(tq), ntau, int(bool(anti)),
+                                        _ptr(u0), _ptr(recl), _stream(self.dev)), "pd_eval_u0")
+        return u0, recl, ntau
+
+    def eval_u(self, tau, phi, anti, nt, want_last):
+        tq, _ = self._tau_points(tau)
+        ntau = tq.shape[1]
+        ph = torch.as_tensor(phi, dtype=_F64, device=self.dev) if not isinstance(phi, torch.Tensor) \
+            else phi.to(device=self.dev, dtype=_F64)
+        if ph.ndim == 0:
+            ph = ph[None]
+        if ph.ndim != 1:
+            raise ValueError("phi must be a scalar or a 1-D array.")
+        ph = ph.contiguous()
+        nphi = ph.shape[0]
+        u = torch.empty((self.B, self.NQuad, ntau, nphi), dtype=_F64, device=self.dev)
+        ulast = torch.empty((self.B, self.NQuad, ntau), dtype=_F64, device=self.dev) if want_last else None
+        st = self._state()
+        self._check(self.lib.pd_eval_u(ctypes.byref(self.cfg), ctypes.byref(st), _ptr(tq), ntau, _ptr(ph), nphi,
+                                       int(bool(anti)), int(bool(nt)), _ptr(self.omega), _ptr(self.f),
+                                       _ptr(self.leg_all), _ptr(self.omega_s), _ptr(self.wleg), _ptr(u), _ptr(ulast),
+                                       _stream(self.dev)), "pd_eval_u")
+        return u, ulast, ph, ntau, nphi
+
+
+def _bc_tensor(b, name, B, N, NF, batched, T):
+    """Dirichlet boundary values as [B, NFb, N] (pydisort.py:199-202, :274-285)."""
+    t = T(b)
+    if t.numel() == 0 or bool((t == 0).all()):
+        return torch.zeros((B, 1, N), dtype=_F64, device=t.device)
+    which = "bottom" if name == "b_pos" else "top"
+    err = ValueError(f"The shape of the {which} boundary condition is incorrect.")
+    if t.numel() == 1 and t.ndim <= 1:
+        return t.reshape(1, 1, 1).expand(B, 1, N).contiguous()
+    if batched:
+        if t.ndim == 1 and t.shape[0] == B:
+            return t[:, None, None].expand(B, 1, N).contiguous()
+        if t.ndim == 2 and t.shape == (B, 1):
+            return t[:, :, None].expand(B, 1, N).contiguous()
+        if t.ndim == 2 and t.shape == (B, N):
+            return t[:, None, :].contiguous()
+        if t.ndim == 3 and t.shape == (B, N, NF):
+            return t.transpose(1, 2).contiguous()
+    if t.ndim == 1 and t.shape[0] == N:
+        return t[None, None, :].expand(B, 1, N).contiguous()
+    if t.ndim == 2 and t.shape == (N, NF):
+        return t.t()[None].expand(B, NF, N).contiguous()
+    raise err
+
+
+def _bdrf_tables(modes, B, N, mu_pos, mu0_host, beam, batched):
+    """Tabulate the BDRF Fourier modes at the quadrature nodes
+    (_solve_for_coeffs.py:121-134): q[(B), NBDRF, N, N], q0[(B), NBDRF, N]."""
+    n = len(modes)
+    qs, q0s, percol = [], [], False
+    mu0_same = mu0_host is None or np.all(mu0_host == mu0_host[0])
+    for fm in modes:
+        if isinstance(fm, TabulatedBDRF):
+            q = fm.q
+            if fm.q0 is None:
+                q0 = np.zeros((N, 1))
+            else:
+                q0 = fm.q0
+            if q0.shape[1] not in (1, B):
+                raise ValueError("TabulatedBDRF.q0 must have 1 or B columns.")
+            q0 = q0.T  # [k, N]
+        elif callable(fm):
+            q = np.asarray(fm(mu_pos, mu_pos), dtype=float)
+            if beam:
+                pts = mu0_host[:1] if mu0_same else mu0_host
+                q0 = np.asarray(fm(mu_pos, np.asarray(pts)), dtype=float).T  # [k, N]
+            else:
+                q0 = np.zeros((1, N))
+        else:
+            a = fm.detach().cpu().numpy() if isinstance(fm, torch.Tensor) else np.asarray(fm, dtype=float)
+            if a.ndim == 0:
+                q = np.full((N, N), float(a))
+                q0 = np.full((1, N), float(a))
+            elif batched and a.shape == (B,):
+                q = np.broadcast_to(a[:, None, None], (B, N, N))
+                q0 = np.broadcast_to(a[:, None], (B, N))
+            else:
+                raise ValueError("BDRF Fourier modes must be scalars, callables, TabulatedBDRF or [B] arrays.")
+        if q.ndim == 3 or q0.shape[0] > 1:
+            percol = True
+        qs.append(q)
+        q0s.append(q0)
+    if not percol:
+        return np.stack(qs)[None].reshape(1, n, N, N), np.stack([x[0] for x in q0s])[None], False
+    Q = np.empty((B, n, N, N))
+    Q0 = np.empty((B, n, N))
+    for m in range(n):
+        Q[:, m] = qs[m] if qs[m].ndim == 3 else qs[m][None]
+        Q0[:, m] = q0s[m] if q0s[m].shape[0] == B else q0s[m][:1]
+    return Q, Q0, True
+
+
+def pydisort(
+    tau_arr, omega_arr,
+    NQuad,
+    Leg_coeffs_all,
+    mu0, I0, phi0,
+    NLeg=None,
+    NFourier=None,
+    b_pos=0,
+    b_neg=0,
+    only_flux=False,
+    f_arr=0,
+    NT_cor=False,
+    BDRF_Fourier_modes=[],
+    s_poly_coeffs=np.array([[]]),
+    use_banded_solver_NLayers=10,
+    autograd_compatible=False,
+):
+    """Solve the 1-D RTE for a column or a batch of columns on the GPU.
+
+    Arguments, defaults, input checks and returned functions follow the
+    reference ``PythonicDISORT.pydisort`` (pydisort.py:13-128); see the module
+    docstring for the batch extension.  Returns
+    ``(mu_arr, flux_up, flux_down, u0)`` plus ``u`` unless ``only_flux``.
+    ``use_banded_solver_NLayers`` is accepted and validated but unused (one
+    block-banded solver covers both of the reference's LAPACK paths)."""
+    if autograd_compatible:
+        raise NotImplementedError("autograd_compatible=True is not supported by the CUDA implementation.")
+    lib, dev = _backend()
+    ins = (tau_arr, omega_arr, Leg_coeffs_all, mu0, I0, phi0, b_pos, b_neg, f_arr, s_poly_coeffs)
+    want_torch = any(_is_dev_tensor(x) for x in ins)
+
+    def T(x):
+        if isinstance(x, torch.Tensor):
+            return x.to(device=dev, dtype=_F64, non_blocking=True)
+        return torch.as_tensor(np.asarray(x, dtype=np.float64)).to(dev, non_blocking=True)
+
+    # ---- shapes (pydisort.py:184-217) ------------------------------------------
+    tau = T(tau_arr)
+    batched = tau.ndim == 2
+    if tau.ndim == 0:
+        tau = tau[None]
+    if tau.ndim == 1:
+        tau = tau[None, :]
+    if tau.ndim != 2:
+        raise ValueError("`tau_arr` must be a scalar, [NLayers] or [B, NLayers].")
+    B, L = tau.shape
+    NQuad = int(NQuad)
+    if NLeg is None:
+        NLeg = NQuad
+    if only_flux:
+        NFourier = 1
+    elif NFourier is None:
+        NFourier = NQuad
+    NLeg, NFourier = int(NLeg), int(NFourier)
+    N = NQuad // 2
+
+    def per_layer(x, trailing, msg):
+        """[..., L, *trailing] with an optional leading B axis -> [B, L, *trailing]."""
+        t = T(x)
+        nd = 1 + len(trailing)
+        if t.ndim == nd - 1 and L == 1:      # a single layer given without its layer axis
+            t = t[None]
+        if t.ndim == nd:
+            if t.shape[0] != L:
+                raise ValueError(msg)
+            return t[None].expand((B,) + tuple(t.shape))
+        if t.ndim == nd + 1 and batched and t.shape[0] == B:
+            if t.shape[1] != L:
+                raise ValueError(msg)
+            return t
+        raise ValueError(msg)
+
+    omega = per_layer(omega_arr, (), "The zeroth dimension of the shape of `omega_arr` does not match the number of "
+                      "layers which is deduced from the length of `tau_arr`.")
+    leg_in = T(Leg_coeffs_all)
+    if leg_in.ndim == 1:
+        leg_in = leg_in[None, :]
+    leg = per_layer(leg_in, (None,), "The zeroth dimension of the shape of `Leg_coeffs_all` does not match the number "
+                    "of layers which is deduced from the length of `tau_arr`.")
+    NLeg_all = leg.shape[-1]
+
+    f_t = T(f_arr)
+    if f_t.ndim == 0:
+        f_t = f_t[None]
+    f_nonzero = bool((f_t != 0).any())
+    if f_nonzero:
+        f = per_layer(f_t, (), "The length of `f_arr` does not match the number of layers which is deduced from the "
+                      "length of `tau_arr`.")
+    else:
+        f = None
+
+    s_t = T(s_poly_coeffs)
+    if s_t.ndim == 1:
+        s_t = s_t[None, :]
+    Ns = 0 if (s_t.numel() == 0 or bool((s_t == 0).all())) else int(s_t.shape[-1])
+    if Ns > 0:
+        s_poly = per_layer(s_t, (None,), "The zeroth dimension of the shape of `s_poly_coeffs` does not match the "
+                           "number of layers which is deduced from the length of `tau_arr`.")
+    else:
+        s_poly = None
+
+    def per_column(x, name):
+        t = T(x)
+        if t.ndim == 0:
+            return t[None].expand(B)
+        if t.ndim == 1 and t.shape[0] == B and (batched or B == 1):
+            return t
+        raise ValueError(f"`{name}` must be a scalar or (batch mode) a [B] array.")
+
+    mu0_t, I0_t, phi0_t = per_column(mu0, "mu0"), per_column(I0, "I0"), per_column(phi0, "phi0")
+
+    # ---- structural checks (pydisort.py:223-291; value checks run on the device) ----
+    if not NLeg > 0:
+        raise ValueError("The number of phase function Legendre coefficients must be positive.")
+    if not NLeg <= NLeg_all:
+        raise ValueError("`NLeg` cannot be larger than the number of phase function Legendre coefficients provided.")
+    if not NQuad >= 2:
+        raise ValueError("There must be at least two streams.")
+    if not NQuad % 2 == 0:
+        raise ValueError("The number of streams must be even.")
+    if not NFourier > 0:
+        raise ValueError("The number of Fourier modes to use in the solution must be positive.")
+    if not NFourier <= NLeg:
+        raise ValueError("The number of Fourier modes to use in the solution must be less than or equal to the "
+                         "number of phase function Legendre coefficients used.")
+    if NFourier > 64 and not only_flux:
+        warnings.warn("`NFourier` is large and may cause errors, consider decreasing `NFourier` to 64 and it "
+                      "probably should be even less. By default `NFourier` equals `NQuad`.")
+    if not NLeg <= NQuad:
+        raise ValueError("There should be more streams than the number of phase function Legendre coefficients used.")
+    if not use_banded_solver_NLayers >= 3:
+        raise ValueError("The minimum threshold `use_banded_solver_NLayers` is 3, else the matrix will not be banded.")
+    bpos = _bc_tensor(b_pos, "b_pos", B, N, NFourier, batched, T)
+    bneg = _bc_tensor(b_neg, "b_neg", B, N, NFourier, batched, T)
+    NFb = max(bpos.shape[1], bneg.shape[1])
+    if bpos.shape[1] != NFb:
+        bpos = torch.cat([bpos, torch.zeros((B, NFb - 1, N), dtype=_F64, device=dev)], dim=1)
+    if bneg.shape[1] != NFb:
+        bneg = torch.cat([bneg, torch.zeros((B, NFb - 1, N), dtype=_F64, device=dev)], dim=1)
+
+    beam = bool((I0_t > 0).any())
+    nt_static = bool(NT_cor) and not only_flux and NLeg < NLeg_all and f is not None
+    mu_h, W_h, mu_d, w_d, ptab = _constants(NQuad, NLeg, NFourier, dev)
+
+    # ---- BDRF tables ---------------------------------------------------------------
+    modes = list(BDRF_Fourier_modes)[:NFourier]
+    NBDRF = len(modes)
+    flags = (_lib.PD_FLAG_BEAM if beam else 0) | (_lib.PD_FLAG_ISO if Ns > 0 else 0) | \
+        (_lib.PD_FLAG_DELTA_M if f is not None else 0)
+    bdrf_q = bdrf_q0 = None
+    if NBDRF:
+        need_mu0 = beam and any(callable(m) and not isinstance(m, TabulatedBDRF) for m in modes)
+        mu0_host = mu0_t.cpu().numpy() if need_mu0 else None
+        q, q0, percol = _bdrf_tables(modes, B, N, mu_h, mu0_host, beam, batched)
+        bdrf_q, bdrf_q0 = T(np.ascontiguousarray(q)), T(np.ascontiguousarray(q0))
+        if percol:
+            flags |= _lib.PD_FLAG_BDRF_PERCOL
+
+    cfg = _lib.pd_config(B, L, NQuad, NLeg, NLeg_all, NFourier, NBDRF, Ns, NFb, flags)
+
+    # ---- device buffers ------------------------------------------------------------
+    sol = _Solution()
+    sol.lib, sol.dev, sol.cfg = lib, dev, cfg
+    sol.B, sol.L, sol.N, sol.NQuad, sol.NF = B, L, N, NQuad, NFourier
+    sol.batched, sol.want_torch = batched, want_torch
+    sol.tau_arr_in = tau_arr
+    sol.tau = tau.contiguous()
+    sol.omega = omega.contiguous()
+    sol.leg_all = leg.contiguous()
+    sol.f = f.contiguous() if f is not None else torch.zeros((B, L), dtype=_F64, device=dev)
+    sol.mu_d, sol.w_d = mu_d, w_d
+    new = lambda *shape: torch.empty(shape, dtype=_F64, device=dev)
+    sol.taus, sol.omega_s, sol.wleg, sol.scale_tau = new(B, L + 1), new(B, L), new(B, L, NLeg), new(B, L)
+    sol.s_s = new(B, L, Ns) if Ns > 0 else None
+    sol.colp = new(B, _lib.PD_NCOLP)
+    bpos_s, bneg_s = new(B, NFb, N), new(B, NFb, N)
+    pmu0 = torch.zeros((B, NFourier, NLeg), dtype=_F64, device=dev)
+    checks = torch.zeros(1, dtype=torch.int32, device=dev)
+    stream = _stream(dev)
+    sp_c = s_poly.contiguous() if s_poly is not None else None
+    rc = lib.pd_prologue(ctypes.byref(cfg), _ptr(sol.tau), _ptr(sol.omega), _ptr(sol.leg_all),
+                         _ptr(f.contiguous()) if f is not None else None, _ptr(sp_c),
+                         _ptr(mu0_t.contiguous()), _ptr(I0_t.contiguous()), _ptr(phi0_t.contiguous()),
+                         _ptr(bpos), _ptr(bneg), _ptr(mu_d), int(bool(NT_cor)),
+                         _ptr(sol.taus), _ptr(sol.omega_s), _ptr(sol.wleg), _ptr(sol.scale_tau), _ptr(sol.s_s),
+                         _ptr(sol.colp), _ptr(bpos_s), _ptr(bneg_s), _ptr(pmu0), _ptr(checks), stream)
+    sol._check(rc, "pd_prologue")
+    _raise_for_checks(int(checks.item()))
+
+    sol.K = new(B, NFourier, L, N)
+    sol.G = new(B, NFourier, L, 2, N, N)
+    sol.Bv = new(B, NFourier, L, NQuad) if beam else None
+    sol.dth = new(B, L, Ns, NQuad) if Ns > 0 else None
+    sol.C = new(B, NFourier, L, NQuad)
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    ws_bytes = lib.pd_workspace_bytes(ctypes.byref(cfg))
+    workspace = torch.empty(max(ws_bytes // 8, 1), dtype=_F64, device=dev)
+    rc = lib.pd_solve(ctypes.byref(cfg), _ptr(sol.taus), _ptr(sol.omega_s), _ptr(sol.wleg), _ptr(sol.s_s),
+                      _ptr(sol.colp), _ptr(bpos_s), _ptr(bneg_s), _ptr(pmu0), _ptr(mu_d), _ptr(w_d), _ptr(ptab),
+                      _ptr(bdrf_q), _ptr(bdrf_q0), _ptr(workspace), ws_bytes, _ptr(sol.K), _ptr(sol.G), _ptr(sol.Bv),
+                      _ptr(sol.dth), _ptr(sol.C), _ptr(status), stream)
+    sol._check(rc, "pd_solve")
+    bad = int(status.max().item())
+    del workspace
+    if bad:
+        nbad = int((status != 0).sum().item())
+        msg = []
+        if bad & _lib.PD_ST_QR_NOCONV:
+            msg.append("the shifted-QR eigen-solver did not converge")
+        if bad & _lib.PD_ST_BAD_EIGEN:
+            msg.append("a reduced eigenvalue k^2 was not positive (the reference would return NaN here)")
+        if bad & _lib.PD_ST_ZERO_PIVOT:
+            msg.append("an exactly singular pivot was met")
+        warnings.warn(f"pydisort_b200: numerical trouble in {nbad} of {B} columns: " + "; ".join(msg) + ".")
+    sol.status = status
+    sol.nt = nt_static
+
+    mu_arr = np.concatenate([mu_h, -mu_h])
+    if want_torch:
+        mu_arr = torch.as_tensor(mu_arr, dtype=_F64, device=dev)
+    outs = _make_functions(sol)
+    return (mu_arr,) + (outs[:3] if only_flux else outs)
+
+
+def _raise_for_checks(chk):
+    C = _lib.CHK
+    if chk & C["TAU_POS"]:
+        raise ValueError("tau values cannot be non-positive.")
+    if chk & C["THICK_POS"]:
+        raise ValueError("Layer thicknesses cannot be non-positive.")
+    if chk & C["OMEGA_RANGE"]:
+        raise ValueError("Single-scattering albedo must be between 0 and 1, excluding 1.")
+    if chk & C["LEG0_FIXED"]:
+        warnings.warn("The zeroth index phase function Legendre coefficient must be, and has been corrected to, 1.")
+    if chk & C["LEG_RANGE"]:
+        raise ValueError("The phase function Legendre coefficients must all be between -1 and 1 exclusive (only the "
+                         "zeroth coefficient can equal 1).")
+    if chk & C["I0_NEG"]:
+        raise ValueError("The intensity of the incident beam cannot be negative.")
+    if chk & C["MU0_RANGE"]:
+        raise ValueError("The cosine of the polar angle of the incident beam must be between 0 and 1, excluding 0.")
+    if chk & C["PHI0_RANGE"]:
+        raise ValueError("Provide the principal azimuthal angle for the incident beam (must be between 0 and 2pi, "
+                         "excluding 2pi).")
+    if chk & C["F_RANGE"]:
+        raise ValueError("The fractional scattering must be between 0 and 1.")
+    if chk & C["MU0_AT_NODE"]:
+        raise ValueError("Some quadrature angles come too close to `mu0`. Perturb `NQuad` or `mu0` to rectify this "
+                         "error.")
+    if chk & C["OMEGA_NEAR1"]:
+        warnings.warn("Some delta-scaled single-scattering albedos are very close to 1 which may cause numerical "
+                      "instability.")
+    if chk & C["LEG_NEAR1"]:
+        warnings.warn("Some delta-scaled phase function Legendre coefficients have a magnitude that is very close "
+                      "to 1 (this excludes the zeroth index coefficient which must be 1) which may cause numerical "
+                      "instability.")
+
+
+def _make_functions(sol):
+    """The output functions, with the reference's signatures
+    (_assemble_intensity_and_fluxes.py:170,334,446,527; pydisort.py:643)."""
+
+    def flux_up(tau, is_antiderivative_wrt_tau=False, return_tau_arr=False):
+        out, ntau = sol.eval_flux(tau, is_antiderivative_wrt_tau)
+        res = sol._finish(out[0], (ntau,))
+        return (res, sol.tau_arr_in) if return_tau_arr else res
+
+    def flux_down(tau, is_antiderivative_wrt_tau=False, return_tau_arr=False):
+        out, ntau = sol.eval_flux(tau, is_antiderivative_wrt_tau)
+        res = (sol._finish(out[1], (ntau,)), sol._finish(out[2], (ntau,)))
+        return res + (sol.tau_arr_in,) if return_tau_arr else res
+
+    def u0(tau, is_antiderivative_wrt_tau=False, return_tau_arr=False, _return_act_dscale_for_reclass=False):
+        val, recl, ntau = sol.eval_u0(tau, is_antiderivative_wrt_tau, _return_act_dscale_for_reclass)
+        outs = (sol._finish(val, (sol.NQuad, ntau)),)
+        if return_tau_arr:
+            outs += (sol.tau_arr_in,)
+        if _return_act_dscale_for_reclass:
+            outs += (sol._finish(recl, (ntau,)),)
+        return outs[0] if len(outs) == 1 else outs
+
+    def u(tau, phi, is_antiderivative_wrt_tau=False, return_Fourier_error=False, return_tau_arr=False):
+        val, ulast, ph, ntau, nphi = sol.eval_u(tau, phi, is_antiderivative_wrt_tau, sol.nt, False)
+        outs = (sol._finish(val, (sol.NQuad, ntau, nphi)),)
+        if return_Fourier_error:
+            # Cauchy criterion on the un-corrected, un-rescaled series (:265-316)
+            plain, ulast, _, _, _ = sol.eval_u(tau, phi, is_antiderivative_wrt_tau, False, True)
+            resc = sol.colp[:, _lib.PD_COL_RESCALE][:, None, None, None]
+            plain = torch.where(resc != 0, plain / resc, torch.zeros_like(plain)).abs()
+            phi0 = sol.colp[:, _lib.PD_COL_PHI0][:, None]
+            last = (ulast[:, :, :, None] * torch.cos((sol.NF - 1) * (phi0 - ph[None, :]))[:, None, None, :]).abs()
+            ratio = torch.where(plain > 1e-8, last / plain, torch.zeros_like(plain))
+            err = ratio.reshape(sol.B, -1).max(dim=1).values
+            if not sol.batched:
+                err = err[0]
+            outs += (err if sol.want_torch else (err.cpu().numpy()[()]),)
+        if return_tau_arr:
+            outs += (sol.tau_arr_in,)
+        return outs[0] if len(outs) == 1 else outs
+
+    for fn, kind in ((flux_up, "flux_up"), (flux_down, "flux_down"), (u0, "u0"), (u, "u")):
+        fn.kind = kind
+        fn.batched = sol.batched
+        fn.solution = sol
+    return flux_up, flux_down, u0, u

@@ -1,0 +1,56 @@
+// pd_common.cuh -- shared definitions for the pydisort_b200 CUDA kernels.
+//
+// All numerical routines are written against a "lane group" policy: a group of
+// G::size threads cooperates on one work item whose matrices live in shared
+// memory; loops are strided by lane and `sync()` orders shared-memory traffic
+// inside the group.  On the GPU a group is a power-of-two slice of a warp
+// (SubWarp<LANES>); SerialGroup (size 1) runs the same code in one thread and
+// is also what the host-side debug build under tests/hostsim compiles.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/pydisort_b200.h"
+
+#if defined(__CUDACC__)
+#define PD_HD __host__ __device__ __forceinline__
+#else
+#define PD_HD inline
+#endif
+
+#define PD_EPS 2.220446049250313e-16
+#define PD_PI 3.141592653589793238462643383279502884
+
+struct SerialGroup {
+    static constexpr int size = 1;
+    PD_HD int lane() const { return 0; }
+    PD_HD void sync() const {}
+};
+
+#if defined(__CUDACC__)
+template <int LANES>
+struct SubWarp {
+    static_assert(LANES >= 1 && LANES <= 32 && (LANES & (LANES - 1)) == 0, "LANES must be a power of two <= 32");
+    static constexpr int size = LANES;
+    unsigned mask;
+    int ln;
+    __device__ __forceinline__ SubWarp() {
+        const int l = threadIdx.x & 31;
+        ln = l & (LANES - 1);
+        mask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (l - ln));
+    }
+    __device__ __forceinline__ int lane() const { return ln; }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+};
+#endif
+
+// padded leading dimension: odd, so that row- and column-wise lane access are both bank-conflict free
+PD_HD int pd_ld(int n) { return n | 1; }
+
+PD_HD double pd_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}

@@ -1,0 +1,339 @@
+// pd_eval.cuh -- evaluation of the solved column at user optical depths:
+//   u^m(tau) = G_l (C_l * exp(K_l (tau* - tau*_{l-1 or l}))) + B_l exp(-tau*/mu0) + delta_m0 v_l(tau*)
+// (_assemble_intensity_and_fluxes.py:170-613), and the Nakajima-Tanaka
+// TMS / IMS intensity corrections (pydisort.py:409-694).
+#pragma once
+#include "pd_common.cuh"
+#include "pd_stage_b.cuh"  // pd_thermal_at
+
+struct PdEval {
+    int B, L, N, NF, Ns, NLeg, NLeg_all;
+    int beam, iso;
+    pd_state st;
+    const double* tau_q;  // [B][ntau]
+    int ntau;
+    int anti;
+};
+
+// first layer whose lower boundary is >= t  (np.argmax(tau <= tau_arr), :185)
+PD_HD int pd_locate(const double* tau_col, int L, double t) {
+    int lo = 0, hi = L - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (t <= tau_col[mid]) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+
+// scaled optical depth of a query point (:189-195); dm = column uses delta-M scaling
+PD_HD double pd_scaled_tau(const PdEval& a, int b, int l, double t) {
+    const double dm = a.st.colp[(long)b * PD_NCOLP + PD_COL_DM];
+    if (dm == 0.0) return t;
+    const double* tau = a.st.tau + (long)b * a.L;
+    const double* taus = a.st.taus + (long)b * (a.L + 1);
+    return taus[l + 1] - (tau[l] - t) * a.st.scale_tau[(long)b * a.L + l];
+}
+
+// u^m at one point into uv[2n] (shared); ev[2n] is scratch.  Includes the beam
+// and (m = 0) thermal particular solutions; NOT multiplied by rescale_factor.
+template <class Grp>
+PD_HD void pd_mode_at(const Grp& g, const PdEval& a, int b, int m, int l, double ts, double* ev, double* uv) {
+    const int lane = g.lane();
+    const int n = a.N, n2 = 2 * n;
+    const long item = ((long)b * a.NF + m) * a.L + l;
+    const double* K = a.st.K + item * n;
+    const double* Gp = a.st.G + item * 2 * n * n;
+    const double* Gm = Gp + n * n;
+    const double* C = a.st.C + item * n2;
+    const double* taus = a.st.taus + (long)b * (a.L + 1);
+    const double sc = a.st.scale_tau[(long)b * a.L + l];
+    const double dtop = ts - taus[l], dbot = ts - taus[l + 1];
+    for (int j = lane; j < n; j += Grp::size) {
+        const double k = K[j];
+        double em = exp(-k * dtop) * C[j], ep = exp(k * dbot) * C[n + j];
+        if (a.anti) {
+            em /= -(sc * k);
+            ep /= (sc * k);
+        }
+        ev[j] = em;
+        ev[n + j] = ep;
+    }
+    g.sync();
+    double eb = 0.0;
+    const bool beam = a.beam && a.st.colp[(long)b * PD_NCOLP + PD_COL_I0] > 0.0;
+    if (beam) {
+        const double mu0 = a.st.colp[(long)b * PD_NCOLP + PD_COL_MU0];
+        eb = exp(-ts / mu0);
+        if (a.anti) eb /= -(sc / mu0);
+    }
+    const double* Bv = beam ? a.st.Bv + item * n2 : nullptr;
+    const double* dth = (a.iso && m == 0) ? a.st.dth + ((long)b * a.L + l) * a.Ns * n2 : nullptr;
+    for (int i = lane; i < n; i += Grp::size) {
+        double top = 0.0, bot = 0.0;
+        for (int j = 0; j < n; ++j) {
+            const double gp = Gp[i * n + j], gm = Gm[i * n + j];
+            top = fma(gp, ev[j], top);
+            top = fma(gm, ev[n + j], top);
+            bot = fma(gm, ev[j], bot);
+            bot = fma(gp, ev[n + j], bot);
+        }
+        if (Bv) {
+            top = fma(Bv[i], eb, top);
+            bot = fma(Bv[n + i], eb, bot);
+        }
+        if (dth) {
+            if (!a.anti) {
+                top += pd_thermal_at(dth, a.Ns, n2, i, ts);
+                bot += pd_thermal_at(dth, a.Ns, n2, n + i, ts);
+            } else {  // sum_q d_q tau*^(q+1) / ((q+1) scale_tau_l)
+                double pt = 0.0, pb = 0.0;
+                for (int q = a.Ns - 1; q >= 0; --q) {
+                    pt = fma(pt, ts, dth[q * n2 + i] / (q + 1));
+                    pb = fma(pb, ts, dth[q * n2 + n + i] / (q + 1));
+                }
+                top += pt * ts / sc;
+                bot += pb * ts / sc;
+            }
+        }
+        uv[i] = top;
+        uv[n + i] = bot;
+    }
+    g.sync();
+}
+
+// fluxes at one point (:446-613).  sm: 4n doubles.
+template <class Grp>
+PD_HD void pd_flux_point(const Grp& g, const PdEval& a, int b, int t, double* sm, double* Fup, double* Fdn,
+                         double* Fdir) {
+    const int n = a.N;
+    const double tq = a.tau_q[(long)b * a.ntau + t];
+    const int l = pd_locate(a.st.tau + (long)b * a.L, a.L, tq);
+    const double ts = pd_scaled_tau(a, b, l, tq);
+    double* ev = sm;
+    double* uv = sm + 2 * n;
+    pd_mode_at(g, a, b, 0, l, ts, ev, uv);
+    if (g.lane() == 0) {
+        double up = 0.0, dn = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double mw = a.st.mu_nodes[i] * a.st.w_nodes[i];
+            up = fma(mw, uv[i], up);
+            dn = fma(mw, uv[n + i], dn);
+        }
+        const double* cp = a.st.colp + (long)b * PD_NCOLP;
+        const double resc = cp[PD_COL_RESCALE];
+        double direct = 0.0, direct_s = 0.0;
+        if (a.beam && cp[PD_COL_I0] > 0.0) {
+            const double mu0 = cp[PD_COL_MU0], I0 = cp[PD_COL_I0];
+            if (a.anti) {
+                const double sc = a.st.scale_tau[(long)b * a.L + l];
+                direct = I0 * mu0 * exp(-tq / mu0) * -mu0;
+                direct_s = I0 * mu0 * exp(-ts / mu0) / (-sc / mu0);
+            } else {
+                direct = I0 * mu0 * exp(-tq / mu0);
+                direct_s = I0 * mu0 * exp(-ts / mu0);
+            }
+        }
+        const long o = (long)b * a.ntau + t;
+        Fup[o] = resc * (2.0 * PD_PI * up);
+        Fdn[o] = resc * (2.0 * PD_PI * dn + direct_s - direct);
+        Fdir[o] = resc * direct;
+    }
+    g.sync();
+}
+
+// u0 at one point (:334-433); recl = actinic delta-scaling reclassification term (:360-371)
+template <class Grp>
+PD_HD void pd_u0_point(const Grp& g, const PdEval& a, int b, int t, double* sm, double* u0, double* recl) {
+    const int n = a.N, n2 = 2 * n;
+    const double tq = a.tau_q[(long)b * a.ntau + t];
+    const int l = pd_locate(a.st.tau + (long)b * a.L, a.L, tq);
+    const double ts = pd_scaled_tau(a, b, l, tq);
+    double* ev = sm;
+    double* uv = sm + n2;
+    pd_mode_at(g, a, b, 0, l, ts, ev, uv);
+    const double* cp = a.st.colp + (long)b * PD_NCOLP;
+    const double resc = cp[PD_COL_RESCALE];
+    for (int i = g.lane(); i < n2; i += Grp::size) u0[((long)b * n2 + i) * a.ntau + t] = resc * uv[i];
+    if (recl && g.lane() == 0) {
+        double r = 0.0;
+        if (cp[PD_COL_DM] != 0.0) {
+            const double mu0 = cp[PD_COL_MU0], I0 = cp[PD_COL_I0];
+            if (a.anti) {
+                const double sc = a.st.scale_tau[(long)b * a.L + l];
+                r = I0 * exp(-ts / mu0) / (-sc / mu0) - I0 * exp(-tq / mu0) * -mu0;
+            } else {
+                r = I0 * exp(-ts / mu0) - I0 * exp(-tq / mu0);
+            }
+        }
+        recl[(long)b * a.ntau + t] = r;
+    }
+    g.sync();
+}
+
+// all Fourier modes at one point into um[NF][2n] (shared); ev: 2n scratch
+template <class Grp>
+PD_HD void pd_all_modes_point(const Grp& g, const PdEval& a, int b, int l, double ts, double* ev, double* um) {
+    for (int m = 0; m < a.NF; ++m) pd_mode_at(g, a, b, m, l, ts, ev, um + m * 2 * a.N);
+}
+
+// ---------------------------------------------------------------------------
+// Nakajima-Tanaka corrections.
+// ---------------------------------------------------------------------------
+struct PdNT {
+    const double* omega;     // [B][L]  unscaled
+    const double* f;         // [B][L]
+    const double* leg_all;   // [B][L][NLeg_all]  (coefficient 0 already forced to 1)
+    const double* omega_s;   // [B][L]
+    const double* wleg;      // [B][L][NLeg]
+};
+
+// sum_{l<nc} coef[l] P_l(x) by upward recurrence (coefficients already carry their (2l+1) weights)
+PD_HD double pd_legendre_series(const double* coef, int nc, double x) {
+    double p0 = 1.0, p1 = x;
+    double s = coef[0];
+    if (nc > 1) s = fma(coef[1], x, s);
+    for (int l = 1; l + 1 < nc; ++l) {
+        const double p2 = ((2 * l + 1) * x * p1 - l * p0) / (l + 1);
+        s = fma(coef[l + 1], p2, s);
+        p0 = p1;
+        p1 = p2;
+    }
+    return s;
+}
+
+// sum_{l<nc} (2l+1) g[l] P_l(x) for unweighted phase-function moments, g[0] taken as 1 (pydisort.py:246-248)
+PD_HD double pd_legendre_series_raw(const double* gl, int nc, double x) {
+    double p0 = 1.0, p1 = x;
+    double s = 1.0;
+    if (nc > 1) s = fma(3.0 * gl[1], x, s);
+    for (int l = 1; l + 1 < nc; ++l) {
+        const double p2 = ((2 * l + 1) * x * p1 - l * p0) / (l + 1);
+        s = fma((2 * l + 3) * gl[l + 1], p2, s);
+        p0 = p1;
+        p1 = p2;
+    }
+    return s;
+}
+
+// Per column pre-computation for the TMS correction, multi-layer part
+// (pydisort.py:495-589): Rpos[n][L], Rneg[n][L] by stable recurrences.
+//   Rpos[i][l] = sum_{r>l} (1-exp(-dt_r (1/mu_i+1/mu0))) exp(-top_r/mu0) exp(-(top_r - bot_l)/mu_i)
+//   Rneg[i][l] = sum_{r<l} term_neg[i][r] exp(-(top_l - bot_r)/mu_i)
+template <class Grp>
+PD_HD void pd_tms_scans(const Grp& g, const PdEval& a, int b, double* Rpos, double* Rneg) {
+    const int n = a.N, L = a.L;
+    const double* taus = a.st.taus + (long)b * (L + 1);
+    const double* scl = a.st.scale_tau + (long)b * L;
+    const double mu0 = a.st.colp[(long)b * PD_NCOLP + PD_COL_MU0];
+    for (int i = g.lane(); i < n; i += Grp::size) {
+        const double mi = 1.0 / a.st.mu_nodes[i];
+        const double mu = a.st.mu_nodes[i];
+        double acc = 0.0;
+        Rpos[i * L + (L - 1)] = 0.0;
+        for (int l = L - 2; l >= 0; --l) {
+            const int r = l + 1;
+            const double dt = taus[r + 1] - taus[r];
+            double term = -expm1(-dt * (mi + 1.0 / mu0)) * exp(-taus[r] / mu0);
+            if (a.anti) term *= mu / scl[r];
+            // contributions of layers below r, attenuated across layer r
+            acc = (l == L - 2) ? term : fma(acc, exp(-dt * mi), term);
+            Rpos[i * L + l] = acc;
+        }
+        acc = 0.0;
+        Rneg[i * L] = 0.0;
+        for (int l = 1; l < L; ++l) {
+            const int r = l - 1;
+            const double dt = taus[r + 1] - taus[r];
+            const double th = dt * (mi - 1.0 / mu0);
+            const double em1 = expm1(-fabs(th));
+            double term = (th >= 0.0) ? -em1 * exp(-taus[r + 1] / mu0) : em1 * exp(-dt * mi) * exp(-taus[r] / mu0);
+            if (a.anti) term *= -mu / scl[r];
+            acc = (l == 1) ? term : fma(acc, exp(-dt * mi), term);
+            Rneg[i * L + l] = acc;
+        }
+    }
+    g.sync();
+}
+
+// Per column IMS constants (pydisort.py:601-611): coefficient array
+// imsc[NLeg_all] = (2l+1)(2 g~_l - g~_l^2), and scalars out[0] = amplitude
+// I0/(4 pi) (w f)^2/(1 - w f), out[1] = scaled mu0.
+template <class Grp>
+PD_HD void pd_ims_setup(const Grp& g, const PdEval& a, const PdNT& nt, int b, double* imsc, double* out) {
+    const int L = a.L;
+    const double* tau = a.st.tau + (long)b * L;
+    const double* om = nt.omega + (long)b * L;
+    const double* f = nt.f + (long)b * L;
+    double s1 = 0.0, st = 0.0, s2 = 0.0;
+    for (int l = 0; l < L; ++l) {
+        s1 += om[l] * tau[l];
+        st += tau[l];
+        s2 += f[l] * om[l] * tau[l];
+    }
+    const double wavg = s1 / st, favg = s2 / s1;
+    for (int k = g.lane(); k < a.NLeg_all; k += Grp::size) {
+        double acc = 0.0;
+        for (int l = 0; l < L; ++l) {
+            const double res = (k < a.NLeg) ? f[l] : nt.leg_all[((long)b * L + l) * a.NLeg_all + k];
+            acc += res * om[l] * tau[l];
+        }
+        const double r = acc / s2;
+        imsc[k] = (2 * k + 1) * (2.0 * r - r * r);
+    }
+    if (g.lane() == 0) {
+        const double* cp = a.st.colp + (long)b * PD_NCOLP;
+        out[0] = cp[PD_COL_I0] / (4.0 * PD_PI) * (wavg * favg) * (wavg * favg) / (1.0 - wavg * favg);
+        out[1] = cp[PD_COL_MU0] / (1.0 - wavg * favg);
+    }
+    g.sync();
+}
+
+// TMS + IMS correction of stream i at query point (tq in layer l, scaled ts) and azimuth phi.
+// wall_l: the unweighted phase-function moments g_l[NLeg_all] of layer l.
+PD_HD double pd_nt_value(const PdEval& a, const PdNT& nt, int b, int i, int l, double tq, double ts, double phi,
+                         const double* Rpos, const double* Rneg, const double* imsc, const double* imsv,
+                         const double* wall_l) {
+    const int n = a.N, L = a.L;
+    const double* cp = a.st.colp + (long)b * PD_NCOLP;
+    const double mu0 = cp[PD_COL_MU0], I0 = cp[PD_COL_I0], phi0 = cp[PD_COL_PHI0];
+    const double* taus = a.st.taus + (long)b * (L + 1);
+    const bool up = i < n;
+    const int ii = up ? i : i - n;
+    const double mua = a.st.mu_nodes[ii];
+    const double mus = up ? mua : -mua;  // signed stream cosine
+    const double mi = 1.0 / mua;
+    const double cphi = cos(phi0 - phi);
+    // cosine of the scattering angle between (mus, phi) and the beam (-mu0, phi0)
+    const double nu = -mu0 * mus + sqrt(1.0 - mu0 * mu0) * sqrt(1.0 - mus * mus) * cphi;
+    const double fl = nt.f[(long)b * L + l];
+    const double ptrue = pd_legendre_series_raw(wall_l, a.NLeg_all, nu);
+    const double ptrun = pd_legendre_series(nt.wleg + ((long)b * L + l) * a.NLeg, a.NLeg, nu);
+    const double Bsc = nt.omega_s[(long)b * L + l] * (I0 / (4.0 * PD_PI)) * (mu0 / (mu0 + mus)) * (ptrue / (1.0 - fl) - ptrun);
+    const double sc = a.st.scale_tau[(long)b * L + l];
+    const double ttop = taus[l], tbot = taus[l + 1];
+    double e0 = exp(-ts / mu0);
+    double own, other;
+    if (up) {
+        const double ex = exp((ts - tbot) * mi - tbot / mu0);
+        own = a.anti ? e0 / (-sc / mu0) - ex / (sc * mi) : e0 - ex;
+        other = (L > 1) ? Rpos[ii * L + l] * exp(mi * (ts - tbot)) : 0.0;
+    } else {
+        const double ex = exp((ttop - ts) * mi - ttop / mu0);
+        own = a.anti ? e0 / (-sc / mu0) + ex / (sc * mi) : e0 - ex;
+        other = (L > 1) ? Rneg[ii * L + l] * exp(mi * (ttop - ts)) : 0.0;
+    }
+    double val = Bsc * (own + other);
+    if (!up) {  // IMS, downward streams only (:613-638)
+        const double mu0s = imsv[1];
+        const double nu2 = -mu0 * (-mua) + sqrt(1.0 - mu0 * mu0) * sqrt(1.0 - mua * mua) * cphi;
+        const double x = mi - 1.0 / mu0s;
+        double chi;
+        if (a.anti)
+            chi = ((mu0s - x * mu0s * (mu0s + tq)) * exp(-tq / mu0s) - mua * exp(-tq * mi)) / (mua * mu0s * x * x);
+        else
+            chi = ((tq - 1.0 / x) * exp(-tq / mu0s) + exp(-tq * mi) / x) / (mua * mu0s * x);
+        val += imsv[0] * pd_legendre_series(imsc, a.NLeg_all, nu2) * chi;
+    }
+    return val;
+}

@@ -1,0 +1,398 @@
+// pd_kernels.cu -- __global__ kernels and the extern "C" entry points of
+// libpydisort_b200.so (declared in include/pydisort_b200.h).  sm_100a only.
+#include <cuda_runtime.h>
+
+#include "pd_eval.cuh"
+#include "pd_prologue.cuh"
+#include "pd_stage_a.cuh"
+#include "pd_stage_b.cuh"
+
+#define PD_NUM_SMS 148            // B200
+#define PD_SMEM_BUDGET (200 * 1024)  // per-SM shared memory we plan residency against
+#define PD_SMEM_MAX_CTA (227 * 1024)
+
+static inline int pd_lanes_for(int n) {
+    int l = 1;
+    while (l < n && l < 32) l <<= 1;
+    return l;
+}
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ============================================================================
+// prologue
+// ============================================================================
+__global__ void __launch_bounds__(128) k_prologue(PdPrologue a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= a.B) return;
+    SubWarp<32> g;
+    int chk = pd_prologue_column(g, a, warp);
+    chk = __reduce_or_sync(0xffffffffu, chk);
+    if (chk && g.lane() == 0) atomicOr(a.checks, chk);
+}
+
+// ============================================================================
+// stage A: one lane group per (column, layer) item, one Fourier mode per blockIdx.y
+// ============================================================================
+template <int LANES>
+__global__ void k_stage_a(PdStageA a, const double* __restrict__ ptab, int items_per_cta, int item_doubles) {
+    extern __shared__ double smem[];
+    const int m = blockIdx.y;
+    const int n = a.N, nm = a.NLeg - m;
+    double* Q = smem;  // [nm][n] scaled Legendre table of this mode
+    for (int idx = threadIdx.x; idx < nm * n; idx += blockDim.x) {
+        const int i = idx % n;
+        Q[idx] = ptab[((long)m * a.NLeg + m) * n + idx] * sqrt(a.w[i] / a.mu[i]);
+    }
+    __syncthreads();
+    const int gi = threadIdx.x / LANES;
+    const long it = (long)blockIdx.x * items_per_cta + gi;
+    if (gi >= items_per_cta || it >= (long)a.B * a.L) return;
+    SubWarp<LANES> g;
+    double* sm = smem + ((nm * n + 1) & ~1) + (long)gi * item_doubles;
+    pd_stage_a_item(g, a, (int)(it / a.L), m, (int)(it % a.L), Q, sm);
+}
+
+struct StageAPlan {
+    int lanes, items_per_cta, item_doubles, threads;
+    size_t smem;
+};
+static StageAPlan plan_stage_a(int N, int NLeg) {
+    StageAPlan p;
+    p.lanes = pd_lanes_for(N);
+    p.item_doubles = (pd_stage_a_item_doubles(N, NLeg) + 1) & ~1;
+    const size_t qbytes = (size_t)((NLeg * N + 1) & ~1) * 8;
+    int ipc = 128 / p.lanes;
+    while (ipc > 1 && qbytes + (size_t)ipc * p.item_doubles * 8 > 96 * 1024) ipc >>= 1;
+    p.items_per_cta = ipc;
+    p.threads = ipc * p.lanes < 32 ? 32 : ipc * p.lanes;
+    p.smem = qbytes + (size_t)ipc * p.item_doubles * 8;
+    return p;
+}
+
+template <int LANES>
+static cudaError_t launch_stage_a(const PdStageA& a, const double* ptab, const StageAPlan& p, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(k_stage_a<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return e;
+    const long items = (long)a.B * a.L;
+    dim3 grid((unsigned)((items + p.items_per_cta - 1) / p.items_per_cta), a.NF);
+    k_stage_a<LANES><<<grid, p.threads, p.smem, st>>>(a, ptab, p.items_per_cta, p.item_doubles);
+    return cudaGetLastError();
+}
+
+// ============================================================================
+// stage B: one warp per (column, mode) system, persistent grid, per-warp history slot
+// ============================================================================
+__global__ void k_stage_b(PdStageB a, double* hist, long hist_doubles, int sys_doubles) {
+    extern __shared__ double smem[];
+    const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5;
+    const long slot = (long)blockIdx.x * wpb + w;
+    const long nslots = (long)gridDim.x * wpb;
+    SubWarp<32> g;
+    double* sm = smem + (long)w * sys_doubles;
+    double* h = hist + slot * hist_doubles;
+    const long nsys = (long)a.B * a.NF;
+    for (long s = slot; s < nsys; s += nslots) pd_stage_b_system(g, a, (int)(s / a.NF), (int)(s % a.NF), sm, h);
+}
+
+struct StageBPlan {
+    int wpb, sys_doubles, blocks;
+    size_t smem;
+    long hist_doubles, slots;
+};
+static StageBPlan plan_stage_b(int B, int NF, int N, int L) {
+    StageBPlan p;
+    p.sys_doubles = (pd_stage_b_doubles(N) + 1) & ~1;
+    const size_t per_warp = (size_t)p.sys_doubles * 8;
+    int wpb = 4;
+    while (wpb > 1 && per_warp * wpb > 64 * 1024) wpb >>= 1;
+    p.wpb = wpb;
+    p.smem = per_warp * wpb;
+    int ctas_per_sm = (int)(PD_SMEM_BUDGET / p.smem);
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm * wpb > 16) ctas_per_sm = 16 / wpb;
+    const long nsys = (long)B * NF;
+    long blocks = (nsys + wpb - 1) / wpb;
+    if (blocks > (long)PD_NUM_SMS * ctas_per_sm) blocks = (long)PD_NUM_SMS * ctas_per_sm;
+    p.blocks = (int)blocks;
+    p.slots = blocks * wpb;
+    p.hist_doubles = pd_stage_b_history_doubles(N, L);
+    return p;
+}
+
+// ============================================================================
+// evaluation kernels
+// ============================================================================
+template <int LANES>
+__global__ void k_eval_flux(PdEval a, double* Fup, double* Fdn, double* Fdir) {
+    extern __shared__ double smem[];
+    const int gpc = blockDim.x / LANES, gi = threadIdx.x / LANES;
+    const long pt = (long)blockIdx.x * gpc + gi;
+    if (pt >= (long)a.B * a.ntau) return;
+    SubWarp<LANES> g;
+    pd_flux_point(g, a, (int)(pt / a.ntau), (int)(pt % a.ntau), smem + (long)gi * 4 * a.N, Fup, Fdn, Fdir);
+}
+
+template <int LANES>
+__global__ void k_eval_u0(PdEval a, double* u0, double* recl) {
+    extern __shared__ double smem[];
+    const int gpc = blockDim.x / LANES, gi = threadIdx.x / LANES;
+    const long pt = (long)blockIdx.x * gpc + gi;
+    if (pt >= (long)a.B * a.ntau) return;
+    SubWarp<LANES> g;
+    pd_u0_point(g, a, (int)(pt / a.ntau), (int)(pt % a.ntau), smem + (long)gi * 4 * a.N, u0, recl);
+}
+
+// u(tau, phi) = sum_m u^m(tau) cos(m (phi0 - phi))   (:256-260)
+template <int LANES>
+__global__ void k_eval_u(PdEval a, const double* __restrict__ phi_q, int nphi, int group_doubles, double* u,
+                         double* ulast) {
+    extern __shared__ double smem[];
+    const int gpc = blockDim.x / LANES, gi = threadIdx.x / LANES;
+    const long pt = (long)blockIdx.x * gpc + gi;
+    if (pt >= (long)a.B * a.ntau) return;
+    SubWarp<LANES> g;
+    const int b = (int)(pt / a.ntau), t = (int)(pt % a.ntau);
+    const int n2 = 2 * a.N;
+    double* ev = smem + (long)gi * group_doubles;
+    double* um = ev + n2;
+    const double tq = a.tau_q[pt];
+    const int l = pd_locate(a.st.tau + (long)b * a.L, a.L, tq);
+    const double ts = pd_scaled_tau(a, b, l, tq);
+    pd_all_modes_point(g, a, b, l, ts, ev, um);
+    const double* cp = a.st.colp + (long)b * PD_NCOLP;
+    const double resc = cp[PD_COL_RESCALE], phi0 = cp[PD_COL_PHI0];
+    for (int idx = g.lane(); idx < n2 * nphi; idx += LANES) {
+        const int i = idx / nphi, p = idx - i * nphi;
+        const double dphi = phi0 - phi_q[p];
+        double s = 0.0;
+        for (int m = 0; m < a.NF; ++m) s += um[m * n2 + i] * cos((double)m * dphi);
+        u[(((long)b * n2 + i) * a.ntau + t) * nphi + p] = resc * s;
+    }
+    if (ulast)
+        for (int i = g.lane(); i < n2; i += LANES) ulast[((long)b * n2 + i) * a.ntau + t] = um[(a.NF - 1) * n2 + i];
+}
+
+// Nakajima-Tanaka corrections added to u in place: one CTA per column.
+__global__ void __launch_bounds__(256) k_nt(PdEval a, PdNT nt, const double* __restrict__ phi_q, int nphi, double* u) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x;
+    const int n = a.N, n2 = 2 * n, L = a.L;
+    double* Rpos = smem;                 // [n][L]
+    double* Rneg = Rpos + n * L;         // [n][L]
+    double* imsc = Rneg + n * L;         // [NLeg_all]
+    double* imsv = imsc + a.NLeg_all;    // [2]
+    if (a.st.colp[(long)b * PD_NCOLP + PD_COL_NT] == 0.0) return;  // gate of pydisort.py:375, column part
+    if (threadIdx.x < 32) {
+        SubWarp<32> g;
+        if (L > 1) pd_tms_scans(g, a, b, Rpos, Rneg);
+        pd_ims_setup(g, a, nt, b, imsc, imsv);
+    }
+    __syncthreads();
+    const double resc = a.st.colp[(long)b * PD_NCOLP + PD_COL_RESCALE];
+    const long total = (long)a.ntau * n2 * nphi;
+    for (long idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int p = (int)(idx % nphi);
+        const int i = (int)((idx / nphi) % n2);
+        const int t = (int)(idx / ((long)nphi * n2));
+        const double tq = a.tau_q[(long)b * a.ntau + t];
+        const int l = pd_locate(a.st.tau + (long)b * L, L, tq);
+        const double ts = pd_scaled_tau(a, b, l, tq);
+        const double v = pd_nt_value(a, nt, b, i, l, tq, ts, phi_q[p], Rpos, Rneg, imsc, imsv,
+                                     nt.leg_all + ((long)b * L + l) * a.NLeg_all);
+        u[(((long)b * n2 + i) * a.ntau + t) * nphi + p] += resc * v;
+    }
+}
+
+// ============================================================================
+// FP64 FMA throughput probe
+// ============================================================================
+__global__ void __launch_bounds__(256) k_fp64_probe(double* sink, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double x = 0.999999, y = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, x, y); a1 = fma(a1, x, y); a2 = fma(a2, x, y); a3 = fma(a3, x, y);
+        a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[0] = s;
+}
+
+// ============================================================================
+// C ABI
+// ============================================================================
+extern "C" {
+
+int pd_abi_version(void) { return PD_ABI_VERSION; }
+
+static int check_cfg(const pd_config* c) {
+    if (!c) return -1;
+    if (c->B < 1 || c->L < 1) return -2;
+    if (c->NQuad < 2 || (c->NQuad & 1)) return -3;
+    if (c->NLeg < 1 || c->NLeg > c->NQuad || c->NLeg > c->NLeg_all) return -4;
+    if (c->NFourier < 1 || c->NFourier > c->NLeg) return -5;
+    if (c->NBDRF < 0 || c->Nscoeffs < 0) return -6;
+    if (c->NFb != 1 && c->NFb != c->NFourier) return -7;
+    if (c->NQuad > 128) return -8;
+    return 0;
+}
+
+size_t pd_workspace_bytes(const pd_config* cfg) {
+    if (check_cfg(cfg)) return 0;
+    const StageBPlan p = plan_stage_b(cfg->B, cfg->NFourier, cfg->NQuad / 2, cfg->L);
+    return (size_t)p.slots * p.hist_doubles * 8;
+}
+
+int pd_prologue(const pd_config* cfg, const double* tau, const double* omega, const double* leg_all, const double* f,
+                const double* s_poly, const double* mu0, const double* I0, const double* phi0, const double* b_pos,
+                const double* b_neg, const double* mu_nodes, int nt_requested, double* taus, double* omega_s,
+                double* wleg, double* scale_tau, double* s_s, double* colp, double* bpos_s, double* bneg_s,
+                double* pmu0, int32_t* checks, void* stream) {
+    if (int e = check_cfg(cfg)) return e;
+    PdPrologue a;
+    a.B = cfg->B; a.L = cfg->L; a.N = cfg->NQuad / 2; a.NLeg = cfg->NLeg; a.NLeg_all = cfg->NLeg_all;
+    a.NF = cfg->NFourier; a.Ns = cfg->Nscoeffs; a.NFb = cfg->NFb; a.nt_requested = nt_requested;
+    a.tau = tau; a.omega = omega; a.leg_all = leg_all; a.f = f; a.s_poly = s_poly; a.mu0 = mu0; a.I0 = I0;
+    a.phi0 = phi0; a.b_pos = b_pos; a.b_neg = b_neg; a.mu_nodes = mu_nodes;
+    a.taus = taus; a.omega_s = omega_s; a.wleg = wleg; a.scale_tau = scale_tau; a.s_s = s_s; a.colp = colp;
+    a.bpos_s = bpos_s; a.bneg_s = bneg_s; a.pmu0 = pmu0; a.checks = checks;
+    cudaError_t e = cudaMemsetAsync(checks, 0, sizeof(int32_t), S(stream));
+    if (e != cudaSuccess) return (int)e;
+    const int wpb = 4;
+    k_prologue<<<(cfg->B + wpb - 1) / wpb, wpb * 32, 0, S(stream)>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int pd_solve(const pd_config* cfg, const double* taus, const double* omega_s, const double* wleg, const double* s_s,
+             const double* colp, const double* bpos_s, const double* bneg_s, const double* pmu0,
+             const double* mu_nodes, const double* w_nodes, const double* ptab, const double* bdrf_q,
+             const double* bdrf_q0, void* workspace, size_t workspace_bytes, double* K, double* G, double* Bv,
+             double* dth, double* C, int32_t* status, void* stream) {
+    if (int e = check_cfg(cfg)) return e;
+    const int N = cfg->NQuad / 2;
+    const StageBPlan pb = plan_stage_b(cfg->B, cfg->NFourier, N, cfg->L);
+    if (workspace_bytes < (size_t)pb.slots * pb.hist_doubles * 8 || !workspace) return -20;
+    if (pb.smem > PD_SMEM_MAX_CTA) return -21;
+    cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int32_t) * cfg->B, S(stream));
+    if (e != cudaSuccess) return (int)e;
+
+    PdStageA a;
+    a.B = cfg->B; a.L = cfg->L; a.N = N; a.NLeg = cfg->NLeg; a.NF = cfg->NFourier; a.Ns = cfg->Nscoeffs;
+    a.beam = (cfg->flags & PD_FLAG_BEAM) != 0; a.iso = (cfg->flags & PD_FLAG_ISO) != 0;
+    a.omega_s = omega_s; a.wleg = wleg; a.s_s = s_s; a.colp = colp; a.pmu0 = pmu0; a.mu = mu_nodes; a.w = w_nodes;
+    a.K = K; a.G = G; a.Bv = Bv; a.dth = dth; a.status = status;
+    const StageAPlan pa = plan_stage_a(N, cfg->NLeg);
+    if (pa.smem > PD_SMEM_MAX_CTA) return -22;
+    switch (pa.lanes) {
+        case 1: e = launch_stage_a<1>(a, ptab, pa, S(stream)); break;
+        case 2: e = launch_stage_a<2>(a, ptab, pa, S(stream)); break;
+        case 4: e = launch_stage_a<4>(a, ptab, pa, S(stream)); break;
+        case 8: e = launch_stage_a<8>(a, ptab, pa, S(stream)); break;
+        case 16: e = launch_stage_a<16>(a, ptab, pa, S(stream)); break;
+        default: e = launch_stage_a<32>(a, ptab, pa, S(stream)); break;
+    }
+    if (e != cudaSuccess) return (int)e;
+
+    PdStageB sb;
+    sb.B = cfg->B; sb.L = cfg->L; sb.N = N; sb.NF = cfg->NFourier; sb.Ns = cfg->Nscoeffs; sb.NBDRF = cfg->NBDRF;
+    sb.NFb = cfg->NFb; sb.beam = a.beam; sb.iso = a.iso; sb.bdrf_percol = (cfg->flags & PD_FLAG_BDRF_PERCOL) != 0;
+    sb.taus = taus; sb.colp = colp; sb.bpos = bpos_s; sb.bneg = bneg_s; sb.mu = mu_nodes; sb.w = w_nodes;
+    sb.bdrf_q = bdrf_q; sb.bdrf_q0 = bdrf_q0; sb.K = K; sb.G = G; sb.Bv = Bv; sb.dth = dth; sb.C = C;
+    sb.status = status;
+    e = cudaFuncSetAttribute(k_stage_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb.smem);
+    if (e != cudaSuccess) return (int)e;
+    k_stage_b<<<pb.blocks, pb.wpb * 32, pb.smem, S(stream)>>>(sb, (double*)workspace, pb.hist_doubles, pb.sys_doubles);
+    return (int)cudaGetLastError();
+}
+
+static PdEval make_eval(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau, int anti) {
+    PdEval a;
+    a.B = cfg->B; a.L = cfg->L; a.N = cfg->NQuad / 2; a.NF = cfg->NFourier; a.Ns = cfg->Nscoeffs;
+    a.NLeg = cfg->NLeg; a.NLeg_all = cfg->NLeg_all;
+    a.beam = (cfg->flags & PD_FLAG_BEAM) != 0; a.iso = (cfg->flags & PD_FLAG_ISO) != 0;
+    a.st = *st; a.tau_q = tau_q; a.ntau = ntau; a.anti = anti;
+    return a;
+}
+
+#define PD_DISPATCH_LANES(lanes, ...)                           \
+    switch (lanes) {                                            \
+        case 1: { constexpr int LN = 1; __VA_ARGS__; } break;   \
+        case 2: { constexpr int LN = 2; __VA_ARGS__; } break;   \
+        case 4: { constexpr int LN = 4; __VA_ARGS__; } break;   \
+        case 8: { constexpr int LN = 8; __VA_ARGS__; } break;   \
+        case 16: { constexpr int LN = 16; __VA_ARGS__; } break; \
+        default: { constexpr int LN = 32; __VA_ARGS__; } break; \
+    }
+
+int pd_eval_flux(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau, int anti, double* Fup,
+                 double* Fdn_diffuse, double* Fdn_direct, void* stream) {
+    if (int e = check_cfg(cfg)) return e;
+    if (ntau < 1) return -30;
+    const PdEval a = make_eval(cfg, st, tau_q, ntau, anti);
+    const int lanes = pd_lanes_for(a.N), threads = 128, gpc = threads / lanes;
+    const long pts = (long)a.B * ntau;
+    const size_t smem = (size_t)gpc * 4 * a.N * 8;
+    const unsigned grid = (unsigned)((pts + gpc - 1) / gpc);
+    PD_DISPATCH_LANES(lanes, (k_eval_flux<LN><<<grid, threads, smem, S(stream)>>>(a, Fup, Fdn_diffuse, Fdn_direct)));
+    return (int)cudaGetLastError();
+}
+
+int pd_eval_u0(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau, int anti, double* u0,
+               double* recl, void* stream) {
+    if (int e = check_cfg(cfg)) return e;
+    if (ntau < 1) return -30;
+    const PdEval a = make_eval(cfg, st, tau_q, ntau, anti);
+    const int lanes = pd_lanes_for(a.N), threads = 128, gpc = threads / lanes;
+    const long pts = (long)a.B * ntau;
+    const size_t smem = (size_t)gpc * 4 * a.N * 8;
+    const unsigned grid = (unsigned)((pts + gpc - 1) / gpc);
+    PD_DISPATCH_LANES(lanes, (k_eval_u0<LN><<<grid, threads, smem, S(stream)>>>(a, u0, recl)));
+    return (int)cudaGetLastError();
+}
+
+int pd_eval_u(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau, const double* phi_q, int nphi,
+              int anti, int nt, const double* omega, const double* f, const double* leg_all, const double* omega_s,
+              const double* wleg, double* u, double* ulast, void* stream) {
+    if (int e = check_cfg(cfg)) return e;
+    if (ntau < 1 || nphi < 1) return -30;
+    const PdEval a = make_eval(cfg, st, tau_q, ntau, anti);
+    const int lanes = pd_lanes_for(a.N);
+    const int group_doubles = (a.NF + 1) * 2 * a.N;
+    int gpc = 128 / lanes;
+    while (gpc > 1 && (size_t)gpc * group_doubles * 8 > 96 * 1024) gpc >>= 1;
+    const size_t smem = (size_t)gpc * group_doubles * 8;
+    if (smem > PD_SMEM_MAX_CTA) return -31;
+    const int threads = gpc * lanes < 32 ? 32 : gpc * lanes;
+    const long pts = (long)a.B * ntau;
+    const unsigned grid = (unsigned)((pts + gpc - 1) / gpc);
+    cudaError_t e = cudaSuccess;
+    PD_DISPATCH_LANES(lanes, {
+        e = cudaFuncSetAttribute(k_eval_u<LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            k_eval_u<LN><<<grid, threads, smem, S(stream)>>>(a, phi_q, nphi, group_doubles, u, ulast);
+    });
+    if (e != cudaSuccess) return (int)e;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    if (nt) {
+        if (!omega || !f || !leg_all || !omega_s || !wleg) return -32;
+        PdNT p;
+        p.omega = omega; p.f = f; p.leg_all = leg_all; p.omega_s = omega_s; p.wleg = wleg;
+        const size_t sm2 = (size_t)(2 * a.N * a.L + a.NLeg_all + 2) * 8;
+        if (sm2 > PD_SMEM_MAX_CTA) return -33;
+        e = cudaFuncSetAttribute(k_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+        if (e != cudaSuccess) return (int)e;
+        k_nt<<<a.B, 256, sm2, S(stream)>>>(a, p, phi_q, nphi, u);
+        e = cudaGetLastError();
+    }
+    return (int)e;
+}
+
+double pd_fp64_probe(double* sink, int iters, void* stream) {
+    const int blocks = PD_NUM_SMS * 8, threads = 256;
+    k_fp64_probe<<<blocks, threads, 0, S(stream)>>>(sink, iters);
+    if (cudaGetLastError() != cudaSuccess) return -1.0;
+    return 2.0 * 8.0 * (double)iters * blocks * threads;
+}
+
+}  // extern "C"

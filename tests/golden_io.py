@@ -57,9 +57,18 @@ def stamnes(file):
     return np.load(os.path.join(GOLDEN, "stamnes", file))
 
 
-def parity(mine, ref, floor=1e-3):
+def group_scale(refs):
+    """Common magnitude of a family of outputs (e.g. diffuse and direct downward
+    flux): a diffuse flux that is physically zero at the top of the atmosphere
+    comes out of the reference as +-1e-16 noise and has no scale of its own."""
+    vals = [np.max(np.abs(np.asarray(r, dtype=float)[np.isfinite(r)]), initial=0.0) for r in refs]
+    return max(vals) if vals else 0.0
+
+
+def parity(mine, ref, floor=1e-3, scale=None):
     """(scale-relative error, worst pointwise relative error over entries with
-    |ref| > floor * max|ref|, number of non-finite reference entries masked)."""
+    |ref| > floor * scale, number of non-finite reference entries masked);
+    scale defaults to max|ref|."""
     mine = np.asarray(mine, dtype=float)
     ref = np.asarray(ref, dtype=float)
     if mine.shape != ref.shape:  # e.g. the reference returns a scalar 0 direct flux when there is no beam
@@ -67,7 +76,8 @@ def parity(mine, ref, floor=1e-3):
     ok = np.isfinite(ref)
     if not ok.any():
         return 0.0, 0.0, int(ref.size)
-    scale = np.max(np.abs(ref[ok]))
+    if scale is None:
+        scale = np.max(np.abs(ref[ok]))
     if scale == 0:
         return float(np.max(np.abs(mine[ok]))), 0.0, int((~ok).sum())
     err = np.abs(mine - ref)

@@ -1,0 +1,160 @@
+// pd_hostsim.cpp -- TEST INFRASTRUCTURE ONLY (never built or loaded by the package).
+//
+// Compiles the very same device routines (pythonic_disort_b200/csrc/*.cuh) for
+// the host with SerialGroup (one "lane") and exposes them under the C ABI of
+// include/pydisort_b200.h, pointers being HOST pointers.  The CPU test-suite
+// uses it to check the kernels' arithmetic and the Python host logic where no
+// GPU exists; it says nothing about intra-warp synchronisation, which only the
+// -m gpu tests (and compute-sanitizer on the GPU box) exercise.
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../pythonic_disort_b200/csrc/pd_eval.cuh"
+#include "../../pythonic_disort_b200/csrc/pd_prologue.cuh"
+#include "../../pythonic_disort_b200/csrc/pd_stage_a.cuh"
+#include "../../pythonic_disort_b200/csrc/pd_stage_b.cuh"
+
+extern "C" {
+
+int pd_abi_version(void) { return PD_ABI_VERSION; }
+int pd_is_hostsim(void) { return 1; }
+
+size_t pd_workspace_bytes(const pd_config* cfg) {
+    return (size_t)pd_stage_b_history_doubles(cfg->NQuad / 2, cfg->L) * 8;
+}
+
+int pd_prologue(const pd_config* cfg, const double* tau, const double* omega, const double* leg_all, const double* f,
+                const double* s_poly, const double* mu0, const double* I0, const double* phi0, const double* b_pos,
+                const double* b_neg, const double* mu_nodes, int nt_requested, double* taus, double* omega_s,
+                double* wleg, double* scale_tau, double* s_s, double* colp, double* bpos_s, double* bneg_s,
+                double* pmu0, int32_t* checks, void*) {
+    PdPrologue a;
+    a.B = cfg->B; a.L = cfg->L; a.N = cfg->NQuad / 2; a.NLeg = cfg->NLeg; a.NLeg_all = cfg->NLeg_all;
+    a.NF = cfg->NFourier; a.Ns = cfg->Nscoeffs; a.NFb = cfg->NFb; a.nt_requested = nt_requested;
+    a.tau = tau; a.omega = omega; a.leg_all = leg_all; a.f = f; a.s_poly = s_poly; a.mu0 = mu0; a.I0 = I0;
+    a.phi0 = phi0; a.b_pos = b_pos; a.b_neg = b_neg; a.mu_nodes = mu_nodes;
+    a.taus = taus; a.omega_s = omega_s; a.wleg = wleg; a.scale_tau = scale_tau; a.s_s = s_s; a.colp = colp;
+    a.bpos_s = bpos_s; a.bneg_s = bneg_s; a.pmu0 = pmu0; a.checks = checks;
+    int chk = 0;
+    SerialGroup g;
+    for (int b = 0; b < cfg->B; ++b) chk |= pd_prologue_column(g, a, b);
+    *checks = chk;
+    return 0;
+}
+
+int pd_solve(const pd_config* cfg, const double* taus, const double* omega_s, const double* wleg, const double* s_s,
+             const double* colp, const double* bpos_s, const double* bneg_s, const double* pmu0,
+             const double* mu_nodes, const double* w_nodes, const double* ptab, const double* bdrf_q,
+             const double* bdrf_q0, void* workspace, size_t, double* K, double* G, double* Bv, double* dth, double* C,
+             int32_t* status, void*) {
+    const int N = cfg->NQuad / 2;
+    memset(status, 0, sizeof(int32_t) * cfg->B);
+    PdStageA a;
+    a.B = cfg->B; a.L = cfg->L; a.N = N; a.NLeg = cfg->NLeg; a.NF = cfg->NFourier; a.Ns = cfg->Nscoeffs;
+    a.beam = (cfg->flags & PD_FLAG_BEAM) != 0; a.iso = (cfg->flags & PD_FLAG_ISO) != 0;
+    a.omega_s = omega_s; a.wleg = wleg; a.s_s = s_s; a.colp = colp; a.pmu0 = pmu0; a.mu = mu_nodes; a.w = w_nodes;
+    a.K = K; a.G = G; a.Bv = Bv; a.dth = dth; a.status = status;
+    SerialGroup g;
+    double* sm = (double*)malloc(sizeof(double) * (pd_stage_a_item_doubles(N, cfg->NLeg) + 16));
+    double* Q = (double*)malloc(sizeof(double) * cfg->NLeg * N);
+    for (int m = 0; m < cfg->NFourier; ++m) {
+        const int nm = cfg->NLeg - m;
+        for (int idx = 0; idx < nm * N; ++idx)
+            Q[idx] = ptab[((long)m * cfg->NLeg + m) * N + idx] * sqrt(w_nodes[idx % N] / mu_nodes[idx % N]);
+        for (int b = 0; b < cfg->B; ++b)
+            for (int l = 0; l < cfg->L; ++l) pd_stage_a_item(g, a, b, m, l, Q, sm);
+    }
+    free(sm);
+    free(Q);
+    PdStageB sb;
+    sb.B = cfg->B; sb.L = cfg->L; sb.N = N; sb.NF = cfg->NFourier; sb.Ns = cfg->Nscoeffs; sb.NBDRF = cfg->NBDRF;
+    sb.NFb = cfg->NFb; sb.beam = a.beam; sb.iso = a.iso; sb.bdrf_percol = (cfg->flags & PD_FLAG_BDRF_PERCOL) != 0;
+    sb.taus = taus; sb.colp = colp; sb.bpos = bpos_s; sb.bneg = bneg_s; sb.mu = mu_nodes; sb.w = w_nodes;
+    sb.bdrf_q = bdrf_q; sb.bdrf_q0 = bdrf_q0; sb.K = K; sb.G = G; sb.Bv = Bv; sb.dth = dth; sb.C = C;
+    sb.status = status;
+    double* smb = (double*)malloc(sizeof(double) * (pd_stage_b_doubles(N) + 16));
+    for (int b = 0; b < cfg->B; ++b)
+        for (int m = 0; m < cfg->NFourier; ++m) pd_stage_b_system(g, sb, b, m, smb, (double*)workspace);
+    free(smb);
+    return 0;
+}
+
+static PdEval make_eval(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau, int anti) {
+    PdEval a;
+    a.B = cfg->B; a.L = cfg->L; a.N = cfg->NQuad / 2; a.NF = cfg->NFourier; a.Ns = cfg->Nscoeffs;
+    a.NLeg = cfg->NLeg; a.NLeg_all = cfg->NLeg_all;
+    a.beam = (cfg->flags & PD_FLAG_BEAM) != 0; a.iso = (cfg->flags & PD_FLAG_ISO) != 0;
+    a.st = *st; a.tau_q = tau_q; a.ntau = ntau; a.anti = anti;
+    return a;
+}
+
+int pd_eval_flux(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau, int anti, double* Fup,
+                 double* Fdn_diffuse, double* Fdn_direct, void*) {
+    const PdEval a = make_eval(cfg, st, tau_q, ntau, anti);
+    SerialGroup g;
+    double* sm = (double*)malloc(sizeof(double) * 4 * a.N);
+    for (int b = 0; b < a.B; ++b)
+        for (int t = 0; t < ntau; ++t) pd_flux_point(g, a, b, t, sm, Fup, Fdn_diffuse, Fdn_direct);
+    free(sm);
+    return 0;
+}
+
+int pd_eval_u0(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau, int anti, double* u0,
+               double* recl, void*) {
+    const PdEval a = make_eval(cfg, st, tau_q, ntau, anti);
+    SerialGroup g;
+    double* sm = (double*)malloc(sizeof(double) * 4 * a.N);
+    for (int b = 0; b < a.B; ++b)
+        for (int t = 0; t < ntau; ++t) pd_u0_point(g, a, b, t, sm, u0, recl);
+    free(sm);
+    return 0;
+}
+
+int pd_eval_u(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau, const double* phi_q, int nphi,
+              int anti, int nt, const double* omega, const double* f, const double* leg_all, const double* omega_s,
+              const double* wleg, double* u, double* ulast, void*) {
+    const PdEval a = make_eval(cfg, st, tau_q, ntau, anti);
+    SerialGroup g;
+    const int n = a.N, n2 = 2 * n, L = a.L;
+    double* ev = (double*)malloc(sizeof(double) * (a.NF + 1) * n2);
+    double* um = ev + n2;
+    double* scr = (double*)malloc(sizeof(double) * (2 * n * L + a.NLeg_all + 2));
+    double *Rpos = scr, *Rneg = scr + n * L, *imsc = scr + 2 * n * L, *imsv = imsc + a.NLeg_all;
+    PdNT p;
+    p.omega = omega; p.f = f; p.leg_all = leg_all; p.omega_s = omega_s; p.wleg = wleg;
+    for (int b = 0; b < a.B; ++b) {
+        const double* cp = st->colp + (long)b * PD_NCOLP;
+        const double resc = cp[PD_COL_RESCALE], phi0 = cp[PD_COL_PHI0];
+        const int ntb = nt && cp[PD_COL_NT] != 0.0;
+        if (ntb) {
+            if (L > 1) pd_tms_scans(g, a, b, Rpos, Rneg);
+            pd_ims_setup(g, a, p, b, imsc, imsv);
+        }
+        for (int t = 0; t < ntau; ++t) {
+            const double tq = tau_q[(long)b * ntau + t];
+            const int l = pd_locate(st->tau + (long)b * L, L, tq);
+            const double ts = pd_scaled_tau(a, b, l, tq);
+            pd_all_modes_point(g, a, b, l, ts, ev, um);
+            for (int i = 0; i < n2; ++i) {
+                for (int q = 0; q < nphi; ++q) {
+                    const double dphi = phi0 - phi_q[q];
+                    double s = 0.0;
+                    for (int m = 0; m < a.NF; ++m) s += um[m * n2 + i] * cos((double)m * dphi);
+                    double v = resc * s;
+                    if (ntb)
+                        v += resc * pd_nt_value(a, p, b, i, l, tq, ts, phi_q[q], Rpos, Rneg, imsc, imsv,
+                                                leg_all + ((long)b * L + l) * a.NLeg_all);
+                    u[(((long)b * n2 + i) * ntau + t) * nphi + q] = v;
+                }
+                if (ulast) ulast[((long)b * n2 + i) * ntau + t] = um[(a.NF - 1) * n2 + i];
+            }
+        }
+    }
+    free(ev);
+    free(scr);
+    return 0;
+}
+
+double pd_fp64_probe(double*, int, void*) { return -1.0; }
+
+}  // extern "C"

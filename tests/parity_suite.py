@@ -1,0 +1,91 @@
+"""Parity checks shared by the CPU (host build of the kernels) and GPU test files."""
+import os
+import warnings
+
+import numpy as np
+
+import golden_io
+from pythonic_disort_b200 import synthetic
+from pythonic_disort_b200.subroutines import _compare
+
+
+def to_np(x):
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
+
+
+def check_suite_record_outputs(pydisort, name, max_records=None, base_tol=1e-9):
+    """Every evaluation the reference test `name` performs, against the reference's own FP64 output."""
+    records, _ = golden_io.load_test(name)
+    worst = 0.0
+    for rec in records[:max_records]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = pydisort(*rec["args"], **rec["kwargs"])
+        tol = golden_io.conditioning_tolerance(rec["args"][1], base_tol)
+        for call, got in golden_io.run_calls(out, rec):
+            scale = golden_io.group_scale(call["outs"])
+            for g, r in zip(got, call["outs"]):
+                err, _, _ = golden_io.parity(np.squeeze(to_np(g)), np.squeeze(r), scale=scale)
+                assert err <= tol, (name, call["fn"], "anti" if call["anti"] else "", err, tol)
+                worst = max(worst, err / tol)
+    return worst
+
+
+def check_stamnes(pydisort, name):
+    """The reference suite's own pass criteria against DISORT 4.0.99 (pydisotest/1_test.py:78-81)."""
+    records, compares = golden_io.load_test(name)
+    results = []
+    for cmp in compares:
+        rec = records[cmp["record"]]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = pydisort(*rec["args"], **rec["kwargs"])
+        results.append(_compare(golden_io.stamnes(cmp["file"]), cmp["mu_to_compare"], cmp["reorder_mu"],
+                                out[1], out[2], out[4] if cmp["has_u"] else None))
+    if name == "9corrections":  # pydisotest/9_test.py:368-370
+        plain, corrected = results
+        assert np.mean(plain[0] - corrected[0]) > 0
+        assert np.mean(plain[2] - corrected[2]) > 0
+        assert np.mean(plain[6] - corrected[6]) > 0
+        return
+    for res in results:
+        for d, ratio in zip(res[0:6:2], res[1:6:2]):
+            assert np.max(ratio[d > 1e-3], initial=0) < 1e-3
+        if len(res) > 6:
+            assert np.max(res[7][res[6] > 1e-3], initial=0) < 1e-2
+
+
+def run_batched(pydisort, ens):
+    """One batched call + evaluation on the ensemble's grid -> dict of numpy arrays [B, ...]."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = pydisort(*ens["args"], **ens["kwargs"])
+    t = ens["tau_eval"]
+    dn = out[2](t)
+    res = dict(flux_up=to_np(out[1](t)), flux_down_diffuse=to_np(dn[0]), flux_down_direct=to_np(dn[1]),
+               u0=to_np(out[3](t)))
+    if "u" in ens["outputs"]:
+        res["u"] = to_np(out[4](t, ens["phi_eval"]))
+    return res
+
+
+def compare_fields(got, ref, ncol, tol=1e-9, label=""):
+    """Per column and field: max|X - X_ref| <= tol * scale; returns the worst ratio and the
+    worst pointwise-relative error over entries larger than 1e-3 of the field's scale."""
+    worst, worst_pw, masked = 0.0, 0.0, 0
+    for b in range(ncol):
+        fscale = golden_io.group_scale([ref[k][b] for k in ("flux_up", "flux_down_diffuse", "flux_down_direct")])
+        for key in got:
+            scale = fscale if key.startswith("flux") else None
+            err, pw, nmask = golden_io.parity(got[key][b], ref[key][b], scale=scale)
+            assert err <= tol, (label, key, b, err)
+            worst, worst_pw, masked = max(worst, err), max(worst_pw, pw), masked + nmask
+    return worst, worst_pw, masked
+
+
+def check_ensemble_vs_golden(pydisort, name, tol=1e-9):
+    gold = np.load(os.path.join(golden_io.GOLDEN, f"ensemble_{name}.npz"))
+    ncol = int(gold["ncol"])
+    ens = synthetic.make(name, ncol)
+    got = run_batched(pydisort, ens)
+    return compare_fields(got, {k: gold[k] for k in got}, ncol, tol, name)
