@@ -123,6 +123,21 @@ int pd_solve(const pd_config* cfg,
              double* K, double* G, double* Bv, double* dth, double* C, int32_t* status,
              void* stream);
 
+/* Same as pd_solve but runs only the stages selected in `stages`
+ * (PD_STAGE_EIGEN: per-(column, mode, layer) eigen-decomposition and particular
+ * solutions -> K, G, Bv, dth;  PD_STAGE_BC: per-(column, mode) boundary-condition
+ * solve -> C).  Lets callers time or re-run the two kernels separately. */
+#define PD_STAGE_EIGEN 1
+#define PD_STAGE_BC    2
+int pd_solve_stages(const pd_config* cfg, int stages,
+             const double* taus, const double* omega_s, const double* wleg, const double* s_s,
+             const double* colp, const double* bpos_s, const double* bneg_s, const double* pmu0,
+             const double* mu_nodes, const double* w_nodes, const double* ptab,
+             const double* bdrf_q, const double* bdrf_q0,
+             void* workspace, size_t workspace_bytes,
+             double* K, double* G, double* Bv, double* dth, double* C, int32_t* status,
+             void* stream);
+
 /* Output functions evaluated at ntau optical depths per column
  * (tau_q[B][ntau], unscaled tau as the user gives it; each value must lie in
  * [0, tau_L], checked by the caller).  `anti` != 0 selects the tau-antiderivative.

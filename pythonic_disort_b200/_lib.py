@@ -33,7 +33,7 @@ CHK = dict(TAU_POS=1 << 0, THICK_POS=1 << 1, OMEGA_RANGE=1 << 2, LEG_RANGE=1 << 
            PHI0_RANGE=1 << 6, F_RANGE=1 << 7, LEG0_FIXED=1 << 8, OMEGA_NEAR1=1 << 9, LEG_NEAR1=1 << 10,
            MU0_AT_NODE=1 << 11)
 
-EXPORTS = ["pd_abi_version", "pd_workspace_bytes", "pd_prologue", "pd_solve", "pd_eval_flux", "pd_eval_u0",
+EXPORTS = ["pd_abi_version", "pd_workspace_bytes", "pd_prologue", "pd_solve", "pd_solve_stages", "pd_eval_flux", "pd_eval_u0",
            "pd_eval_u", "pd_fp64_probe"]
 
 
@@ -70,6 +70,8 @@ def bind(path):
     lib.pd_prologue.argtypes = [cfgp] + [vp] * 11 + [ci] + [vp] * 10 + [vp]
     lib.pd_solve.restype = ci
     lib.pd_solve.argtypes = [cfgp] + [vp] * 13 + [vp, ctypes.c_size_t] + [vp] * 6 + [vp]
+    lib.pd_solve_stages.restype = ci
+    lib.pd_solve_stages.argtypes = [cfgp, ci] + [vp] * 13 + [vp, ctypes.c_size_t] + [vp] * 6 + [vp]
     lib.pd_eval_flux.restype = ci
     lib.pd_eval_flux.argtypes = [cfgp, stp, vp, ci, ci, vp, vp, vp, vp]
     lib.pd_eval_u0.restype = ci

@@ -37,6 +37,14 @@ from .subroutines import Gauss_Legendre_quad, TabulatedBDRF
 _F64 = torch.float64
 _test_backend = None  # set by tests/hostsim only: (ctypes lib, torch.device("cpu"))
 _const_cache = {}
+_profile = None  # bench.py sets this to a list to collect (label, CUDA event) marks around each launch
+
+
+def _mark(label, dev):
+    if _profile is not None and dev.type == "cuda":
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(dev))
+        _profile.append((label, ev))
 
 
 def _backend():
@@ -146,8 +154,10 @@ class _Solution:
         ntau = tq.shape[1]
         out = torch.empty((3, self.B, ntau), dtype=_F64, device=self.dev)
         st = self._state()
+        _mark("begin", self.dev)
         self._check(self.lib.pd_eval_flux(ctypes.byref(self.cfg), ctypes.byref(st), _ptr(tq), ntau, int(bool(anti)),
                                           _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream(self.dev)), "pd_eval_flux")
+        _mark("eval_flux", self.dev)
         return out, ntau
 
     def eval_u0(self, tau, anti, want_recl):
@@ -156,8 +166,10 @@ class _Solution:
         u0 = torch.empty((self.B, self.NQuad, ntau), dtype=_F64, device=self.dev)
         recl = torch.empty((self.B, ntau), dtype=_F64, device=self.dev) if want_recl else None
         st = self._state()
+        _mark("begin", self.dev)
         self._check(self.lib.pd_eval_u0(ctypes.byref(self.cfg), ctypes.byref(st), _ptr(tq), ntau, int(bool(anti)),
                                         _ptr(u0), _ptr(recl), _stream(self.dev)), "pd_eval_u0")
+        _mark("eval_u0", self.dev)
         return u0, recl, ntau
 
     def eval_u(self, tau, phi, anti, nt, want_last):
@@ -174,10 +186,12 @@ class _Solution:
         u = torch.empty((self.B, self.NQuad, ntau, nphi), dtype=_F64, device=self.dev)
         ulast = torch.empty((self.B, self.NQuad, ntau), dtype=_F64, device=self.dev) if want_last else None
         st = self._state()
+        _mark("begin", self.dev)
         self._check(self.lib.pd_eval_u(ctypes.byref(self.cfg), ctypes.byref(st), _ptr(tq), ntau, _ptr(ph), nphi,
                                        int(bool(anti)), int(bool(nt)), _ptr(self.omega), _ptr(self.f),
                                        _ptr(self.leg_all), _ptr(self.omega_s), _ptr(self.wleg), _ptr(u), _ptr(ulast),
                                        _stream(self.dev)), "pd_eval_u")
+        _mark("eval_u", self.dev)
         return u, ulast, ph, ntau, nphi
 
 
@@ -433,6 +447,7 @@ def pydisort(
     checks = torch.zeros(1, dtype=torch.int32, device=dev)
     stream = _stream(dev)
     sp_c = s_poly.contiguous() if s_poly is not None else None
+    _mark("begin", dev)
     rc = lib.pd_prologue(ctypes.byref(cfg), _ptr(sol.tau), _ptr(sol.omega), _ptr(sol.leg_all),
                          _ptr(f.contiguous()) if f is not None else None, _ptr(sp_c),
                          _ptr(mu0_t.contiguous()), _ptr(I0_t.contiguous()), _ptr(phi0_t.contiguous()),
@@ -440,6 +455,7 @@ def pydisort(
                          _ptr(sol.taus), _ptr(sol.omega_s), _ptr(sol.wleg), _ptr(sol.scale_tau), _ptr(sol.s_s),
                          _ptr(sol.colp), _ptr(bpos_s), _ptr(bneg_s), _ptr(pmu0), _ptr(checks), stream)
     sol._check(rc, "pd_prologue")
+    _mark("prologue", dev)
     _raise_for_checks(int(checks.item()))
 
     sol.K = new(B, NFourier, L, N)
@@ -450,11 +466,15 @@ def pydisort(
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     ws_bytes = lib.pd_workspace_bytes(ctypes.byref(cfg))
     workspace = torch.empty(max(ws_bytes // 8, 1), dtype=_F64, device=dev)
-    rc = lib.pd_solve(ctypes.byref(cfg), _ptr(sol.taus), _ptr(sol.omega_s), _ptr(sol.wleg), _ptr(sol.s_s),
-                      _ptr(sol.colp), _ptr(bpos_s), _ptr(bneg_s), _ptr(pmu0), _ptr(mu_d), _ptr(w_d), _ptr(ptab),
-                      _ptr(bdrf_q), _ptr(bdrf_q0), _ptr(workspace), ws_bytes, _ptr(sol.K), _ptr(sol.G), _ptr(sol.Bv),
-                      _ptr(sol.dth), _ptr(sol.C), _ptr(status), stream)
-    sol._check(rc, "pd_solve")
+    solve_args = (_ptr(sol.taus), _ptr(sol.omega_s), _ptr(sol.wleg), _ptr(sol.s_s), _ptr(sol.colp), _ptr(bpos_s),
+                  _ptr(bneg_s), _ptr(pmu0), _ptr(mu_d), _ptr(w_d), _ptr(ptab), _ptr(bdrf_q), _ptr(bdrf_q0),
+                  _ptr(workspace), ws_bytes, _ptr(sol.K), _ptr(sol.G), _ptr(sol.Bv), _ptr(sol.dth), _ptr(sol.C),
+                  _ptr(status), stream)
+    _mark("begin", dev)
+    sol._check(lib.pd_solve_stages(ctypes.byref(cfg), 1, *solve_args), "pd_solve (eigen stage)")
+    _mark("solve_eigen", dev)
+    sol._check(lib.pd_solve_stages(ctypes.byref(cfg), 2, *solve_args), "pd_solve (boundary-condition stage)")
+    _mark("solve_bc", dev)
     bad = int(status.max().item())
     del workspace
     if bad:

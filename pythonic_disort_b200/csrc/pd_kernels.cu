@@ -263,7 +263,7 @@ int pd_prologue(const pd_config* cfg, const double* tau, const double* omega, co
     return (int)cudaGetLastError();
 }
 
-int pd_solve(const pd_config* cfg, const double* taus, const double* omega_s, const double* wleg, const double* s_s,
+int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const double* omega_s, const double* wleg, const double* s_s,
              const double* colp, const double* bpos_s, const double* bneg_s, const double* pmu0,
              const double* mu_nodes, const double* w_nodes, const double* ptab, const double* bdrf_q,
              const double* bdrf_q0, void* workspace, size_t workspace_bytes, double* K, double* G, double* Bv,
@@ -273,7 +273,8 @@ int pd_solve(const pd_config* cfg, const double* taus, const double* omega_s, co
     const StageBPlan pb = plan_stage_b(cfg->B, cfg->NFourier, N, cfg->L);
     if (workspace_bytes < (size_t)pb.slots * pb.hist_doubles * 8 || !workspace) return -20;
     if (pb.smem > PD_SMEM_MAX_CTA) return -21;
-    cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int32_t) * cfg->B, S(stream));
+    cudaError_t e = cudaSuccess;
+    if (stages & PD_STAGE_EIGEN) e = cudaMemsetAsync(status, 0, sizeof(int32_t) * cfg->B, S(stream));
     if (e != cudaSuccess) return (int)e;
 
     PdStageA a;
@@ -283,7 +284,7 @@ int pd_solve(const pd_config* cfg, const double* taus, const double* omega_s, co
     a.K = K; a.G = G; a.Bv = Bv; a.dth = dth; a.status = status;
     const StageAPlan pa = plan_stage_a(N, cfg->NLeg);
     if (pa.smem > PD_SMEM_MAX_CTA) return -22;
-    switch (pa.lanes) {
+    if (stages & PD_STAGE_EIGEN) switch (pa.lanes) {
         case 1: e = launch_stage_a<1>(a, ptab, pa, S(stream)); break;
         case 2: e = launch_stage_a<2>(a, ptab, pa, S(stream)); break;
         case 4: e = launch_stage_a<4>(a, ptab, pa, S(stream)); break;
@@ -292,6 +293,7 @@ int pd_solve(const pd_config* cfg, const double* taus, const double* omega_s, co
         default: e = launch_stage_a<32>(a, ptab, pa, S(stream)); break;
     }
     if (e != cudaSuccess) return (int)e;
+    if (!(stages & PD_STAGE_BC)) return 0;
 
     PdStageB sb;
     sb.B = cfg->B; sb.L = cfg->L; sb.N = N; sb.NF = cfg->NFourier; sb.Ns = cfg->Nscoeffs; sb.NBDRF = cfg->NBDRF;
@@ -303,6 +305,16 @@ int pd_solve(const pd_config* cfg, const double* taus, const double* omega_s, co
     if (e != cudaSuccess) return (int)e;
     k_stage_b<<<pb.blocks, pb.wpb * 32, pb.smem, S(stream)>>>(sb, (double*)workspace, pb.hist_doubles, pb.sys_doubles);
     return (int)cudaGetLastError();
+}
+
+int pd_solve(const pd_config* cfg, const double* taus, const double* omega_s, const double* wleg, const double* s_s,
+             const double* colp, const double* bpos_s, const double* bneg_s, const double* pmu0,
+             const double* mu_nodes, const double* w_nodes, const double* ptab, const double* bdrf_q,
+             const double* bdrf_q0, void* workspace, size_t workspace_bytes, double* K, double* G, double* Bv,
+             double* dth, double* C, int32_t* status, void* stream) {
+    return pd_solve_stages(cfg, PD_STAGE_EIGEN | PD_STAGE_BC, taus, omega_s, wleg, s_s, colp, bpos_s, bneg_s, pmu0,
+                           mu_nodes, w_nodes, ptab, bdrf_q, bdrf_q0, workspace, workspace_bytes, K, G, Bv, dth, C,
+                           status, stream);
 }
 
 static PdEval make_eval(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau, int anti) {

@@ -42,13 +42,13 @@ int pd_prologue(const pd_config* cfg, const double* tau, const double* omega, co
     return 0;
 }
 
-int pd_solve(const pd_config* cfg, const double* taus, const double* omega_s, const double* wleg, const double* s_s,
-             const double* colp, const double* bpos_s, const double* bneg_s, const double* pmu0,
-             const double* mu_nodes, const double* w_nodes, const double* ptab, const double* bdrf_q,
-             const double* bdrf_q0, void* workspace, size_t, double* K, double* G, double* Bv, double* dth, double* C,
-             int32_t* status, void*) {
+int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const double* omega_s, const double* wleg,
+                    const double* s_s, const double* colp, const double* bpos_s, const double* bneg_s,
+                    const double* pmu0, const double* mu_nodes, const double* w_nodes, const double* ptab,
+                    const double* bdrf_q, const double* bdrf_q0, void* workspace, size_t, double* K, double* G,
+                    double* Bv, double* dth, double* C, int32_t* status, void*) {
     const int N = cfg->NQuad / 2;
-    memset(status, 0, sizeof(int32_t) * cfg->B);
+    if (stages & PD_STAGE_EIGEN) memset(status, 0, sizeof(int32_t) * cfg->B);
     PdStageA a;
     a.B = cfg->B; a.L = cfg->L; a.N = N; a.NLeg = cfg->NLeg; a.NF = cfg->NFourier; a.Ns = cfg->Nscoeffs;
     a.beam = (cfg->flags & PD_FLAG_BEAM) != 0; a.iso = (cfg->flags & PD_FLAG_ISO) != 0;
@@ -57,7 +57,7 @@ int pd_solve(const pd_config* cfg, const double* taus, const double* omega_s, co
     SerialGroup g;
     double* sm = (double*)malloc(sizeof(double) * (pd_stage_a_item_doubles(N, cfg->NLeg) + 16));
     double* Q = (double*)malloc(sizeof(double) * cfg->NLeg * N);
-    for (int m = 0; m < cfg->NFourier; ++m) {
+    for (int m = 0; m < cfg->NFourier && (stages & PD_STAGE_EIGEN); ++m) {
         const int nm = cfg->NLeg - m;
         for (int idx = 0; idx < nm * N; ++idx)
             Q[idx] = ptab[((long)m * cfg->NLeg + m) * N + idx] * sqrt(w_nodes[idx % N] / mu_nodes[idx % N]);
@@ -66,6 +66,7 @@ int pd_solve(const pd_config* cfg, const double* taus, const double* omega_s, co
     }
     free(sm);
     free(Q);
+    if (!(stages & PD_STAGE_BC)) return 0;
     PdStageB sb;
     sb.B = cfg->B; sb.L = cfg->L; sb.N = N; sb.NF = cfg->NFourier; sb.Ns = cfg->Nscoeffs; sb.NBDRF = cfg->NBDRF;
     sb.NFb = cfg->NFb; sb.beam = a.beam; sb.iso = a.iso; sb.bdrf_percol = (cfg->flags & PD_FLAG_BDRF_PERCOL) != 0;
@@ -77,6 +78,15 @@ int pd_solve(const pd_config* cfg, const double* taus, const double* omega_s, co
         for (int m = 0; m < cfg->NFourier; ++m) pd_stage_b_system(g, sb, b, m, smb, (double*)workspace);
     free(smb);
     return 0;
+}
+
+int pd_solve(const pd_config* cfg, const double* taus, const double* omega_s, const double* wleg, const double* s_s,
+             const double* colp, const double* bpos_s, const double* bneg_s, const double* pmu0,
+             const double* mu_nodes, const double* w_nodes, const double* ptab, const double* bdrf_q,
+             const double* bdrf_q0, void* workspace, size_t wsb, double* K, double* G, double* Bv, double* dth, double* C,
+             int32_t* status, void* stream) {
+    return pd_solve_stages(cfg, PD_STAGE_EIGEN | PD_STAGE_BC, taus, omega_s, wleg, s_s, colp, bpos_s, bneg_s, pmu0,
+                           mu_nodes, w_nodes, ptab, bdrf_q, bdrf_q0, workspace, wsb, K, G, Bv, dth, C, status, stream);
 }
 
 static PdEval make_eval(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau, int anti) {

@@ -1,0 +1,81 @@
+"""GPU tests (-m gpu): the CUDA path, called through the C ABI by the Python
+host wrapper, against (a) the golden vectors the unmodified reference produced
+for every evaluation of its own 42-test suite, (b) the Stamnes DISORT 4.0.99
+fixtures with the reference suite's pass criteria, (c) reference outputs on
+subsets of the synthetic ensembles, (d) the oracle run live on more columns.
+
+Tolerance: max|X - X_ref| <= 1e-9 * scale per column and field;
+for omega > 0.9999 the tolerance grows like 1e-13/(1-omega) because the
+reference itself is only reproducible to that level there."""
+import warnings
+
+import numpy as np
+import pytest
+
+import golden_io
+import parity_suite
+import pythonic_disort_b200 as pd
+from pythonic_disort_b200 import api, synthetic
+
+pytestmark = pytest.mark.gpu
+SUITE = golden_io.suite_names()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def cuda_backend():
+    import torch
+    assert torch.cuda.is_available()
+    assert api._test_backend is None, "GPU tests must run the CUDA library, not the host build"
+    yield
+
+
+@pytest.mark.parametrize("name", SUITE)
+def test_reference_suite_outputs(name):
+    parity_suite.check_suite_record_outputs(pd.pydisort, name)
+
+
+@pytest.mark.parametrize("name", [n for n in SUITE if golden_io.load_test(n)[1]])
+def test_stamnes_criteria(name):
+    parity_suite.check_stamnes(pd.pydisort, name)
+
+
+@pytest.mark.parametrize("name", ["sw", "lw", "ha", "tp9c16"])
+def test_ensembles_vs_reference_golden(name):
+    parity_suite.check_ensemble_vs_golden(pd.pydisort, name)
+
+
+@pytest.mark.parametrize("name,ncol,first", [("sw", 48, 1000), ("lw", 256, 5000), ("tp1", 6, 0), ("tp9c", 2, 0)])
+def test_ensembles_vs_live_oracle(name, ncol, first):
+    from oracle import disort_oracle
+    ens = synthetic.make(name, ncol, first)
+    got = parity_suite.run_batched(pd.pydisort, ens)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = synthetic.run_reference_like(disort_oracle.pydisort, ens)
+    tol = golden_io.conditioning_tolerance(ens["args"][1])
+    parity_suite.compare_fields(got, ref, ncol, tol, name)
+
+
+def test_batched_equals_column_by_column():
+    ens = synthetic.make("sw", 5, 77)
+    got = parity_suite.run_batched(pd.pydisort, ens)
+    for b in range(5):
+        args, kwargs = synthetic.column_call(ens, b)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = pd.pydisort(*args, **kwargs)
+        np.testing.assert_allclose(out[1](ens["tau_eval"][b]), got["flux_up"][b], rtol=1e-13, atol=0)
+        np.testing.assert_allclose(out[4](ens["tau_eval"][b], ens["phi_eval"]), got["u"][b], rtol=1e-12, atol=1e-15)
+
+
+def test_cuda_tensor_inputs_give_cuda_outputs():
+    import torch
+    ens = synthetic.make("lw", 16)
+    args = tuple(torch.as_tensor(a, device="cuda") if isinstance(a, np.ndarray) else a for a in ens["args"])
+    kw = dict(ens["kwargs"])
+    kw["s_poly_coeffs"] = torch.as_tensor(kw["s_poly_coeffs"], device="cuda")
+    out = pd.pydisort(*args, **kw)
+    Fp = out[1](torch.as_tensor(ens["tau_eval"], device="cuda"))
+    assert Fp.is_cuda and Fp.shape == (16, 61)
+    ref = parity_suite.run_batched(pd.pydisort, ens)
+    np.testing.assert_allclose(Fp.cpu().numpy(), ref["flux_up"], rtol=1e-14)
