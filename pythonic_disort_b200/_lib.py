@@ -7,11 +7,17 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libpydisort_b200.so")
-SOURCES = ["pd_kernels.cu"]
-HEADERS = ["pd_common.cuh", "pd_linalg.cuh", "pd_stage_a.cuh", "pd_stage_b.cuh", "pd_eval.cuh", "pd_prologue.cuh",
-           os.path.join("..", "..", "include", "pydisort_b200.h")]
+SOURCES = ["pd_api.cu", "pd_kernel_a.cu", "pd_kernel_b.cu", "pd_kernel_eval.cu"]
+
+
+def _headers():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))] + \
+        [os.path.join(HERE, "..", "include", "pydisort_b200.h")]
+
+
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
+BUILD_DIR = os.path.join(HERE, "build")
 
 
 class pd_config(ctypes.Structure):
@@ -41,21 +47,33 @@ def needs_build():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    return any(os.path.getmtime(f) > t for f in [os.path.join(CSRC, x) for x in SOURCES] + _headers())
 
 
 def build(force=False, verbose=False):
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    extra = ["-Xptxas=-v"] if verbose else []
+    procs = []
+    for src in SOURCES:  # one nvcc per translation unit, in parallel
+        obj = os.path.join(BUILD_DIR, src.replace(".cu", ".o"))
+        cmd = ["nvcc"] + NVCC_FLAGS + extra + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs, log = [], []
+    for src, obj, proc in procs:
+        out = proc.communicate()[0]
+        log.append(out)
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+        objs.append(obj)
+    res = subprocess.run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs,
+                         capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print("\n".join(log))
     return LIB_PATH
 
 

@@ -37,10 +37,10 @@ PD_HD double pd_scaled_tau(const PdEval& a, int b, int l, double t) {
 
 // u^m at one point into uv[2n] (shared); ev[2n] is scratch.  Includes the beam
 // and (m = 0) thermal particular solutions; NOT multiplied by rescale_factor.
-template <class Grp>
+template <class Grp, int NC = 0>
 PD_HD void pd_mode_at(const Grp& g, const PdEval& a, int b, int m, int l, double ts, double* ev, double* uv) {
     const int lane = g.lane();
-    const int n = a.N, n2 = 2 * n;
+    const int n = NC > 0 ? NC : a.N, n2 = 2 * n;
     const long item = ((long)b * a.NF + m) * a.L + l;
     const double* K = a.st.K + item * n;
     const double* Gp = a.st.G + item * 2 * n * n;
@@ -103,7 +103,7 @@ PD_HD void pd_mode_at(const Grp& g, const PdEval& a, int b, int m, int l, double
 }
 
 // fluxes at one point (:446-613).  sm: 4n doubles.
-template <class Grp>
+template <class Grp, int NC = 0>
 PD_HD void pd_flux_point(const Grp& g, const PdEval& a, int b, int t, double* sm, double* Fup, double* Fdn,
                          double* Fdir) {
     const int n = a.N;
@@ -112,7 +112,7 @@ PD_HD void pd_flux_point(const Grp& g, const PdEval& a, int b, int t, double* sm
     const double ts = pd_scaled_tau(a, b, l, tq);
     double* ev = sm;
     double* uv = sm + 2 * n;
-    pd_mode_at(g, a, b, 0, l, ts, ev, uv);
+    pd_mode_at<Grp, NC>(g, a, b, 0, l, ts, ev, uv);
     if (g.lane() == 0) {
         double up = 0.0, dn = 0.0;
         for (int i = 0; i < n; ++i) {
@@ -143,7 +143,7 @@ PD_HD void pd_flux_point(const Grp& g, const PdEval& a, int b, int t, double* sm
 }
 
 // u0 at one point (:334-433); recl = actinic delta-scaling reclassification term (:360-371)
-template <class Grp>
+template <class Grp, int NC = 0>
 PD_HD void pd_u0_point(const Grp& g, const PdEval& a, int b, int t, double* sm, double* u0, double* recl) {
     const int n = a.N, n2 = 2 * n;
     const double tq = a.tau_q[(long)b * a.ntau + t];
@@ -151,7 +151,7 @@ PD_HD void pd_u0_point(const Grp& g, const PdEval& a, int b, int t, double* sm, 
     const double ts = pd_scaled_tau(a, b, l, tq);
     double* ev = sm;
     double* uv = sm + n2;
-    pd_mode_at(g, a, b, 0, l, ts, ev, uv);
+    pd_mode_at<Grp, NC>(g, a, b, 0, l, ts, ev, uv);
     const double* cp = a.st.colp + (long)b * PD_NCOLP;
     const double resc = cp[PD_COL_RESCALE];
     for (int i = g.lane(); i < n2; i += Grp::size) u0[((long)b * n2 + i) * a.ntau + t] = resc * uv[i];
@@ -172,9 +172,9 @@ PD_HD void pd_u0_point(const Grp& g, const PdEval& a, int b, int t, double* sm, 
 }
 
 // all Fourier modes at one point into um[NF][2n] (shared); ev: 2n scratch
-template <class Grp>
+template <class Grp, int NC = 0>
 PD_HD void pd_all_modes_point(const Grp& g, const PdEval& a, int b, int l, double ts, double* ev, double* um) {
-    for (int m = 0; m < a.NF; ++m) pd_mode_at(g, a, b, m, l, ts, ev, um + m * 2 * a.N);
+    for (int m = 0; m < a.NF; ++m) pd_mode_at<Grp, NC>(g, a, b, m, l, ts, ev, um + m * 2 * a.N);
 }
 
 // ---------------------------------------------------------------------------

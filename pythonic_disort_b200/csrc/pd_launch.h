@@ -1,0 +1,50 @@
+// pd_launch.h -- private: host-side launchers shared by the translation units of libpydisort_b200.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pd_eval.cuh"
+#include "pd_prologue.cuh"
+#include "pd_stage_a.cuh"
+#include "pd_stage_b.cuh"
+
+#define PD_NUM_SMS 148               // B200
+#define PD_SMEM_BUDGET (200 * 1024)  // per-SM shared memory we plan residency against
+#define PD_SMEM_MAX_CTA (227 * 1024)
+
+static inline int pd_lanes_for(int n) {
+    int l = 1;
+    while (l < n && l < 32) l <<= 1;
+    return l;
+}
+static inline cudaStream_t pd_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+struct StageBPlan {
+    int wpb, sys_doubles, blocks;
+    size_t smem;
+    long hist_doubles, slots;
+};
+StageBPlan pd_plan_stage_b(int B, int NF, int N, int L);
+int pd_check_cfg(const pd_config* c);
+
+// return a cudaError_t (0 = ok) or a negative argument error
+int pd_launch_stage_a(const PdStageA& a, const double* ptab, cudaStream_t st);
+int pd_launch_stage_b(const PdStageB& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+#define PD_DISPATCH_LANES(lanes, ...)                           \
+    switch (lanes) {                                            \
+        case 1: { constexpr int LN = 1; __VA_ARGS__; } break;   \
+        case 2: { constexpr int LN = 2; __VA_ARGS__; } break;   \
+        case 4: { constexpr int LN = 4; __VA_ARGS__; } break;   \
+        case 8: { constexpr int LN = 8; __VA_ARGS__; } break;   \
+        case 16: { constexpr int LN = 16; __VA_ARGS__; } break; \
+        default: { constexpr int LN = 32; __VA_ARGS__; } break; \
+    }
+
+// lane count AND (for the production sizes N = 4, 8, 16) a compile-time N
+#define PD_DISPATCH_N(N, ...)                                                        \
+    switch (N) {                                                                     \
+        case 4: { constexpr int LN = 4, NC = 4; __VA_ARGS__; } break;                \
+        case 8: { constexpr int LN = 8, NC = 8; __VA_ARGS__; } break;                \
+        case 16: { constexpr int LN = 16, NC = 16; __VA_ARGS__; } break;             \
+        default: { constexpr int NC = 0; PD_DISPATCH_LANES(pd_lanes_for(N), __VA_ARGS__); } break; \
+    }

@@ -19,9 +19,10 @@
 // each scaled to unit 2-norm; wr[n] the eigenvalues; Y is n x n scratch,
 // cs 2n scratch, vec n scratch.  Returns PD_ST_* bits.
 // ---------------------------------------------------------------------------
-template <class Grp>
-PD_HD int pd_eig_real(const Grp& g, int n, int ld, double* H, double* Z, double* Y, double* wr, double* cs,
+template <class Grp, int NC = 0>
+PD_HD int pd_eig_real(const Grp& g, int n_rt, int ld_rt, double* H, double* Z, double* Y, double* wr, double* cs,
                       double* vec) {
+    const int n = NC > 0 ? NC : n_rt, ld = NC > 0 ? (NC | 1) : ld_rt;  // NC > 0: size known at compile time
     const int lane = g.lane();
     int status = 0;
 
@@ -253,8 +254,9 @@ PD_HD int pd_eig_real(const Grp& g, int n, int ld, double* H, double* Z, double*
 // Solve A x = b (n x n, leading dimension ld) with partial pivoting; A and b
 // are overwritten, x is returned in b.  Returns PD_ST_ZERO_PIVOT on breakdown.
 // ---------------------------------------------------------------------------
-template <class Grp>
-PD_HD int pd_lu_solve(const Grp& g, int n, int ld, double* A, double* b) {
+template <class Grp, int NC = 0>
+PD_HD int pd_lu_solve(const Grp& g, int n_rt, int ld_rt, double* A, double* b) {
+    const int n = NC > 0 ? NC : n_rt, ld = NC > 0 ? (NC | 1) : ld_rt;
     const int lane = g.lane();
     int status = 0;
     for (int k = 0; k < n; ++k) {

@@ -43,10 +43,10 @@ PD_HD void pd_atomic_or(int32_t* p, int v) {
 }
 
 // Q: this mode's scaled Legendre table [NLeg - m][N] (shared by the CTA); sm: per-item scratch.
-template <class Grp>
+template <class Grp, int NC = 0>
 PD_HD void pd_stage_a_item(const Grp& g, const PdStageA& a, int b, int m, int l, const double* Q, double* sm) {
     const int lane = g.lane();
-    const int n = a.N, ld = pd_ld(n), nm = a.NLeg - m;
+    const int n = NC > 0 ? NC : a.N, ld = pd_ld(n), nm = a.NLeg - m;
     double* A1 = sm;            // (alpha-beta)^, later scratch Y of the eigen-solver, later Gp
     double* A2 = A1 + n * ld;   // (alpha+beta)^
     double* H = A2 + n * ld;    // product -> Schur factor -> U^
@@ -149,7 +149,7 @@ PD_HD void pd_stage_a_item(const Grp& g, const PdStageA& a, int b, int m, int l,
                 rhs[i] = s;
             }
             g.sync();
-            const int st = pd_lu_solve(g, n, ld, Z, rhs);  // rhs <- p^ = (B+ + B-)^
+            const int st = pd_lu_solve<Grp, NC>(g, n, ld, Z, rhs);  // rhs <- p^ = (B+ + B-)^
             if (st && lane == 0) pd_atomic_or(a.status + b, st);
             for (int i = lane; i < n; i += Grp::size) {
                 double s = x1[i] - x2[i];
@@ -161,7 +161,7 @@ PD_HD void pd_stage_a_item(const Grp& g, const PdStageA& a, int b, int m, int l,
             g.sync();
         }
 
-        int st = pd_eig_real(g, n, ld, H, Z, A1, wr, cs, vec);
+        int st = pd_eig_real<Grp, NC>(g, n, ld, H, Z, A1, wr, cs, vec);
         for (int j = 0; j < n; ++j)
             if (!(wr[j] > 0.0)) st |= PD_ST_BAD_EIGEN;
         if (st && lane == 0) pd_atomic_or(a.status + b, st);
@@ -194,7 +194,7 @@ PD_HD void pd_stage_a_item(const Grp& g, const PdStageA& a, int b, int m, int l,
         if (thermal) {  // G^-1 [1/mu; -1/mu] = [y1; -y1],  U^ y1 = D (1/mu)
             for (int i = lane; i < n; i += Grp::size) y1[i] = 1.0 / (dinv[i] * a.mu[i]);
             g.sync();
-            const int st2 = pd_lu_solve(g, n, ld, H, y1);
+            const int st2 = pd_lu_solve<Grp, NC>(g, n, ld, H, y1);
             if (st2 && lane == 0) pd_atomic_or(a.status + b, st2);
         }
         g.sync();

@@ -45,10 +45,10 @@ PD_HD double pd_thermal_at(const double* dth_l, int Ns, int n2, int i, double t)
     return v;
 }
 
-template <class Grp>
+template <class Grp, int NC = 0>
 PD_HD void pd_stage_b_system(const Grp& g, const PdStageB& a, int b, int m, double* sm, double* hist) {
     const int lane = g.lane();
-    const int n = a.N, n2 = 2 * n, L = a.L;
+    const int n = NC > 0 ? NC : a.N, n2 = 2 * n, L = a.L;
     const int ldp = 4 * n + 1, rc = 4 * n;  // rhs column
     double* P = sm;                   // [3n][ldp]
     double* E = P + 3 * n * ldp;      // [2n]  exp(-k dtau*) of layer l (first n) and l+1 (last n)
