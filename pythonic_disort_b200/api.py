@@ -446,11 +446,14 @@ def pydisort(
     pmu0 = torch.zeros((B, NFourier, NLeg), dtype=_F64, device=dev)
     checks = torch.zeros(1, dtype=torch.int32, device=dev)
     stream = _stream(dev)
+    # keep every buffer handed to the library alive (and contiguous) in a local until the call returns
     sp_c = s_poly.contiguous() if s_poly is not None else None
+    f_c = f.contiguous() if f is not None else None
+    mu0_c, I0_c, phi0_c = mu0_t.contiguous(), I0_t.contiguous(), phi0_t.contiguous()
+    bpos, bneg = bpos.contiguous(), bneg.contiguous()
     _mark("begin", dev)
     rc = lib.pd_prologue(ctypes.byref(cfg), _ptr(sol.tau), _ptr(sol.omega), _ptr(sol.leg_all),
-                         _ptr(f.contiguous()) if f is not None else None, _ptr(sp_c),
-                         _ptr(mu0_t.contiguous()), _ptr(I0_t.contiguous()), _ptr(phi0_t.contiguous()),
+                         _ptr(f_c), _ptr(sp_c), _ptr(mu0_c), _ptr(I0_c), _ptr(phi0_c),
                          _ptr(bpos), _ptr(bneg), _ptr(mu_d), int(bool(NT_cor)),
                          _ptr(sol.taus), _ptr(sol.omega_s), _ptr(sol.wleg), _ptr(sol.scale_tau), _ptr(sol.s_s),
                          _ptr(sol.colp), _ptr(bpos_s), _ptr(bneg_s), _ptr(pmu0), _ptr(checks), stream)
