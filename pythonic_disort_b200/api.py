@@ -97,6 +97,15 @@ def _constants(NQuad, NLeg, NF, dev):
     return _const_cache[key]
 
 
+def _content_tag(x):
+    """Cheap 'has this array been modified in place' tag for the flux memo."""
+    if isinstance(x, torch.Tensor):
+        return x._version
+    if isinstance(x, np.ndarray):
+        return hash(x.tobytes()) if x.size <= 4096 else (x.ctypes.data, x.shape, float(x.flat[0]), float(x.flat[-1]))
+    return None
+
+
 def _is_dev_tensor(x):
     return isinstance(x, torch.Tensor) and x.is_cuda
 
@@ -150,6 +159,9 @@ class _Solution:
 
     # -- launches ----------------------------------------------------------------
     def eval_flux(self, tau, anti):
+        memo = getattr(self, "_flux_memo", None)  # flux_up(tau) then flux_down(tau): one launch serves both
+        if memo is not None and memo[0] is tau and memo[1] == bool(anti) and memo[4] == _content_tag(tau):
+            return memo[2], memo[3]
         tq, _ = self._tau_points(tau)
         ntau = tq.shape[1]
         out = torch.empty((3, self.B, ntau), dtype=_F64, device=self.dev)
@@ -158,6 +170,8 @@ class _Solution:
         self._check(self.lib.pd_eval_flux(ctypes.byref(self.cfg), ctypes.byref(st), _ptr(tq), ntau, int(bool(anti)),
                                           _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream(self.dev)), "pd_eval_flux")
         _mark("eval_flux", self.dev)
+        self._flux_memo = (tau, bool(anti), out, ntau, _content_tag(tau)) \
+            if isinstance(tau, (np.ndarray, torch.Tensor)) else None
         return out, ntau
 
     def eval_u0(self, tau, anti, want_recl):
@@ -220,51 +234,44 @@ def _bc_tensor(b, name, B, N, NF, batched, T):
     raise err
 
 
-def _bdrf_tables(modes, B, N, mu_pos, mu0_host, beam, batched):
+def _bdrf_tables(modes, B, N, mu_pos, mu0_t, beam, batched, T):
     """Tabulate the BDRF Fourier modes at the quadrature nodes
-    (_solve_for_coeffs.py:121-134): q[(B), NBDRF, N, N], q0[(B), NBDRF, N]."""
-    n = len(modes)
+    (_solve_for_coeffs.py:121-134) as device tensors q[(B), NBDRF, N, N] and
+    q0[(B), NBDRF, N].  Scalars and per-column albedo arrays are expanded on the
+    device; callables are evaluated once on the host."""
     qs, q0s, percol = [], [], False
-    mu0_same = mu0_host is None or np.all(mu0_host == mu0_host[0])
+    mu0_host = None
     for fm in modes:
         if isinstance(fm, TabulatedBDRF):
-            q = fm.q
-            if fm.q0 is None:
-                q0 = np.zeros((N, 1))
-            else:
-                q0 = fm.q0
-            if q0.shape[1] not in (1, B):
+            q = T(fm.q)[None]
+            q0 = T(fm.q0.T if fm.q0 is not None else np.zeros((1, N)))  # [k, N]
+            if q0.shape[0] not in (1, B):
                 raise ValueError("TabulatedBDRF.q0 must have 1 or B columns.")
-            q0 = q0.T  # [k, N]
         elif callable(fm):
-            q = np.asarray(fm(mu_pos, mu_pos), dtype=float)
+            q = T(np.asarray(fm(mu_pos, mu_pos), dtype=float))[None]
             if beam:
-                pts = mu0_host[:1] if mu0_same else mu0_host
-                q0 = np.asarray(fm(mu_pos, np.asarray(pts)), dtype=float).T  # [k, N]
+                if mu0_host is None:
+                    mu0_host = mu0_t.cpu().numpy()
+                same = bool(np.all(mu0_host == mu0_host[0]))
+                pts = mu0_host[:1] if same else mu0_host
+                q0 = T(np.ascontiguousarray(np.asarray(fm(mu_pos, np.asarray(pts)), dtype=float).T))  # [k, N]
             else:
-                q0 = np.zeros((1, N))
+                q0 = torch.zeros((1, N), dtype=_F64, device=mu0_t.device)
         else:
-            a = fm.detach().cpu().numpy() if isinstance(fm, torch.Tensor) else np.asarray(fm, dtype=float)
+            a = T(fm)
             if a.ndim == 0:
-                q = np.full((N, N), float(a))
-                q0 = np.full((1, N), float(a))
+                q, q0 = a.reshape(1, 1, 1).expand(1, N, N), a.reshape(1, 1).expand(1, N)
             elif batched and a.shape == (B,):
-                q = np.broadcast_to(a[:, None, None], (B, N, N))
-                q0 = np.broadcast_to(a[:, None], (B, N))
+                q, q0 = a[:, None, None].expand(B, N, N), a[:, None].expand(B, N)
             else:
                 raise ValueError("BDRF Fourier modes must be scalars, callables, TabulatedBDRF or [B] arrays.")
-        if q.ndim == 3 or q0.shape[0] > 1:
-            percol = True
+        percol = percol or q.shape[0] > 1 or q0.shape[0] > 1
         qs.append(q)
         q0s.append(q0)
-    if not percol:
-        return np.stack(qs)[None].reshape(1, n, N, N), np.stack([x[0] for x in q0s])[None], False
-    Q = np.empty((B, n, N, N))
-    Q0 = np.empty((B, n, N))
-    for m in range(n):
-        Q[:, m] = qs[m] if qs[m].ndim == 3 else qs[m][None]
-        Q0[:, m] = q0s[m] if q0s[m].shape[0] == B else q0s[m][:1]
-    return Q, Q0, True
+    Bq = B if percol else 1
+    Q = torch.stack([q.expand(Bq, N, N) for q in qs], dim=1).contiguous()
+    Q0 = torch.stack([q0.expand(Bq, N) for q0 in q0s], dim=1).contiguous()
+    return Q, Q0, percol
 
 
 def pydisort(
@@ -418,10 +425,7 @@ def pydisort(
         (_lib.PD_FLAG_DELTA_M if f is not None else 0)
     bdrf_q = bdrf_q0 = None
     if NBDRF:
-        need_mu0 = beam and any(callable(m) and not isinstance(m, TabulatedBDRF) for m in modes)
-        mu0_host = mu0_t.cpu().numpy() if need_mu0 else None
-        q, q0, percol = _bdrf_tables(modes, B, N, mu_h, mu0_host, beam, batched)
-        bdrf_q, bdrf_q0 = T(np.ascontiguousarray(q)), T(np.ascontiguousarray(q0))
+        bdrf_q, bdrf_q0, percol = _bdrf_tables(modes, B, N, mu_h, mu0_t, beam, batched, T)
         if percol:
             flags |= _lib.PD_FLAG_BDRF_PERCOL
 
