@@ -3,6 +3,7 @@
 
 #include "pd_launch.h"
 #include "pd_stage_b_fast.cuh"
+#include "pd_stage_b_row.cuh"
 
 template <int NC>
 __global__ void k_stage_b(PdStageB a, double* hist, long hist_doubles, int sys_doubles) {
@@ -57,6 +58,67 @@ static int fast_ctas_per_sm(size_t smem, int threads) {
     return n;
 }
 
+// register-resident variant (N = 4, 8): one lane per panel row, LS = 16 / 32 lanes per system
+static bool use_reg(int N) {
+    if (N != 4 && N != 8) return false;
+    if (const char* e = getenv("PD_STAGE_B_SMEM"))
+        if (e[0] == '1') return false;
+    if (const char* e = getenv("PD_STAGE_B_GENERIC"))
+        if (e[0] == '1') return false;
+    return true;
+}
+
+template <int N>
+__global__ void __launch_bounds__(128, 4) k_stage_b_reg(PdStageB a, double* hist, long hist_doubles) {
+    extern __shared__ double smem[];
+    constexpr int LS = 4 * N;
+    constexpr int SD = (PdStageBRow<N>::SMEM_DOUBLES + 1) & ~1;
+    const int gpb = blockDim.x / LS, gi = threadIdx.x / LS;
+    const long slot = (long)blockIdx.x * gpb + gi;
+    const long nslots = (long)gridDim.x * gpb;
+    SubWarp<LS> g;
+    double* sm = smem + (long)gi * SD;
+    double* h = hist + slot * hist_doubles;
+    const long nsys = (long)a.B * a.NF;
+    for (long s = slot; s < nsys; s += nslots) pd_stage_b_row<N, LS>(g, a, (int)(s / a.NF), (int)(s % a.NF), sm, h);
+}
+
+template <int N>
+static StageBPlan plan_reg(int B, int NF, int L) {
+    StageBPlan p;
+    constexpr int LS = 4 * N;
+    p.sys_doubles = (PdStageBRow<N>::SMEM_DOUBLES + 1) & ~1;
+    p.wpb = 4;
+    const int gpb = p.wpb * (32 / LS);
+    p.smem = (size_t)p.sys_doubles * 8 * gpb;
+    int ctas_per_sm = (int)(PD_SMEM_BUDGET / p.smem);
+    if (ctas_per_sm * p.wpb > 32) ctas_per_sm = 32 / p.wpb;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    int occ = 0;
+    if (cudaFuncSetAttribute(k_stage_b_reg<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stage_b_reg<N>, p.wpb * 32, p.smem) == cudaSuccess &&
+        occ > 0) {
+        if (occ < ctas_per_sm) ctas_per_sm = occ;
+    } else {
+        cudaGetLastError();
+    }
+    const long nsys = (long)B * NF;
+    long blocks = (nsys + gpb - 1) / gpb;
+    if (blocks > (long)PD_NUM_SMS * ctas_per_sm) blocks = (long)PD_NUM_SMS * ctas_per_sm;
+    p.blocks = (int)blocks;
+    p.slots = blocks * gpb;
+    p.hist_doubles = (long)L * PdStageBRow<N>::HIST_PER_LAYER;
+    return p;
+}
+
+template <int N>
+static int launch_reg(const PdStageB& a, const StageBPlan& pb, void* workspace, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(k_stage_b_reg<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb.smem);
+    if (e != cudaSuccess) return (int)e;
+    k_stage_b_reg<N><<<pb.blocks, pb.wpb * 32, pb.smem, st>>>(a, (double*)workspace, pb.hist_doubles);
+    return (int)cudaGetLastError();
+}
+
 template <int N>
 static StageBPlan plan_fast(int B, int NF, int L, int ls) {
     StageBPlan p;
@@ -86,6 +148,7 @@ static StageBPlan plan_fast(int B, int NF, int L, int ls) {
 }
 
 StageBPlan pd_plan_stage_b(int B, int NF, int N, int L) {
+    if (use_reg(N)) return N == 4 ? plan_reg<4>(B, NF, L) : plan_reg<8>(B, NF, L);
     if (const int ls = fast_lanes(N)) {
         if (N == 4) return plan_fast<4>(B, NF, L, ls);
         if (N == 8) return plan_fast<8>(B, NF, L, ls);
@@ -130,6 +193,7 @@ int pd_launch_stage_b(const PdStageB& a, void* workspace, size_t workspace_bytes
     const StageBPlan pb = pd_plan_stage_b(a.B, a.NF, a.N, a.L);
     if (workspace_bytes < (size_t)pb.slots * pb.hist_doubles * 8 || !workspace) return -20;
     if (pb.smem > PD_SMEM_MAX_CTA) return -21;
+    if (use_reg(a.N)) return a.N == 4 ? launch_reg<4>(a, pb, workspace, st) : launch_reg<8>(a, pb, workspace, st);
     if (const int ls = fast_lanes(a.N)) {
         const int key = a.N * 100 + ls;
         switch (key) {

@@ -1,0 +1,272 @@
+// pd_stage_b_row.cuh -- register-resident boundary-condition solve for N = 4 and 8
+// (production path; pd_stage_b_fast.cuh covers N = 16, pd_stage_b.cuh any N and the host build).
+//
+// Same per-layer panel as the other variants (N carried rows + 2N new rows, 4N
+// columns + right-hand side, partial pivoting over the rows still in play), but
+//   * one group of LS >= 3N lanes per (column, mode) system and LANE = PANEL ROW:
+//     every lane keeps its row (4N+1 doubles) in registers, statically indexed;
+//   * pivot search = two integer warp reductions on |a[j]| of the rows in play;
+//   * the pivot lane publishes its row once to shared memory (128-bit stores,
+//     double-buffered, one __syncwarp per step); every lane reads it back with
+//     128-bit broadcast loads and updates its own row:  a[c] -= (a[j]/piv) * u[c];
+//   * rows are never swapped: a pivot row simply leaves the game (`active = false`);
+//   * Gauss-Jordan: earlier pivot rows keep being updated (in SIMT those lanes would
+//     idle anyway), so after the 2N steps pivot row r holds the rows of
+//     U11^-1 [U12 | y] directly -- no triangular solves, no U in shared memory:
+//     M_l = -row * (1/piv), z_l = rhs * (1/piv) go straight to the history buffer;
+//   * the N rows that were never pivots are the next stage's carry; shifting them by
+//     2N columns is a static register move, the freed lanes load the next interface.
+//
+// Shared memory per system: two row buffers + a few 2N-vectors (~1 KB instead of ~7 KB);
+// per eliminated panel row the LSU sees 2 x 128-bit broadcast wavefronts per 4 FMAs
+// instead of 5 wavefronts per FMA (the shared-memory panel version was LSU bound,
+// profiles/r1_summary*.md).
+#pragma once
+#include <type_traits>
+
+#include "pd_stage_b_fast.cuh"
+
+#if defined(__CUDACC__)
+
+template <int N>
+struct PdStageBRow {
+    static constexpr int N2 = 2 * N, NR = 3 * N, RC = 4 * N, NCOL = 4 * N + 1, LDB = 4 * N + 2, HROW = 2 * N + 1;
+    static constexpr int SMEM_DOUBLES = 2 * LDB + 3 * N2 + N * N;
+    static constexpr long HIST_PER_LAYER = (long)N2 * HROW;
+};
+
+template <int LO, int HI, class F>
+__device__ __forceinline__ void pd_static_for(F&& f) {
+    if constexpr (LO < HI) {
+        f(std::integral_constant<int, LO>{});
+        pd_static_for<LO + 1, HI>(f);
+    }
+}
+
+template <int N, int LS>
+__device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, int m, double* sm, double* hist) {
+    using F = PdStageBRow<N>;
+    static_assert(LS >= 3 * N, "one lane per panel row");
+    constexpr int N2 = F::N2, NR = F::NR, RC = F::RC, NCOL = F::NCOL, LDB = F::LDB, HROW = F::HROW;
+    const int lane = g.lane();
+    const int L = A.L;
+    double* buf = sm;            // [2][LDB] published pivot row (double buffered), 16-byte aligned
+    double* E = buf + 2 * LDB;   // [2N] exp(-k dtau*) of layer l (first N) and l+1 (last N)
+    double* xs = E + N2;         // [2N]
+    double* vt = xs + N2;        // [2N]
+    double* R = vt + N2;         // [N][N]
+
+    const long sys = (long)b * A.NF + m;
+    const double* taus = A.taus + (long)b * (L + 1);
+    const double* Kc = A.K + sys * L * N;
+    const double* Gc = A.G + sys * L * 2 * N * N;
+    const double* Bc = A.beam ? A.Bv + sys * L * N2 : nullptr;
+    const double* dthc = (A.iso && m == 0) ? A.dth + (long)b * L * A.Ns * N2 : nullptr;
+    const double mu0 = A.colp[(long)b * PD_NCOLP + PD_COL_MU0];
+    const double I0 = A.colp[(long)b * PD_NCOLP + PD_COL_I0];
+    const bool beam = A.beam && I0 > 0.0;
+    const bool has_bdrf = A.NBDRF > m;
+    const bool have_b = (m == 0) || (A.NFb > 1);
+    const double* bpos = A.bpos + ((long)b * A.NFb + (A.NFb > 1 ? m : 0)) * N;
+    const double* bneg = A.bneg + ((long)b * A.NFb + (A.NFb > 1 ? m : 0)) * N;
+    const unsigned gbase = (threadIdx.x & 31) - lane;  // first warp lane of this group
+    int status = 0;
+
+    // row r of G_l as stored: G_l[r][cc] = blk[(r >= N) ^ (cc >= N)][r mod N][cc mod N]
+    auto Grow = [&](int l, int r, int half) -> const double* {  // the N entries G_l[r][half*N .. half*N+N)
+        const int rb = r >= N;
+        return Gc + ((long)l * 2 + (rb ^ half)) * N * N + (r - rb * N) * N;
+    };
+
+    if (has_bdrf) {
+        const double* q = A.bdrf_q + ((A.bdrf_percol ? (long)b * A.NBDRF : 0) + m) * N * N;
+        for (int idx = lane; idx < N * N; idx += LS)
+            R[idx] = ((m == 0) ? 2.0 : 1.0) * q[idx] * A.mu[idx % N] * A.w[idx % N];
+    }
+    if (lane < N) E[N + lane] = exp(-Kc[lane] * (taus[1] - taus[0]));
+    g.sync();
+
+    double a[NCOL];        // this lane's panel row; a[RC] is the right-hand side
+    bool active = false;   // row still a pivot candidate
+    bool hasrow = false;   // lane holds a row of the current panel
+    int myj = -1;          // pivot step at which this row was used in the current stage (-1: not a pivot row)
+    double mypinv = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c) a[c] = 0.0;
+
+    // ---- top boundary rows: lanes 0..N-1 (they play the role of the carry of stage 0) ----
+    if (lane < N) {
+        const int r = N + lane;  // downward streams
+        const double* g0 = Grow(0, r, 0);
+        const double* g1 = Grow(0, r, 1);
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            a[c] = g0[c];
+            a[N + c] = g1[c] * E[N + c];
+        }
+        double v = have_b ? bneg[lane] : 0.0;
+        if (beam) v -= Bc[r];
+        if (dthc) v -= pd_thermal_at(dthc, A.Ns, N2, r, taus[0]);
+        a[RC] = v;
+        active = true;
+        hasrow = true;
+    } else if (lane < NR) {
+        myj = 0;  // "freed": takes a new row at stage 0
+    }
+
+    for (int l = 0; l < L; ++l) {
+        const bool last = (l == L - 1);
+        // ---- exponentials of layer l (E[0..N)) and l+1 (E[N..2N)) ----
+        double e_new = 0.0;
+        if (lane < N) e_new = E[N + lane];
+        else if (lane < N2 && !last) e_new = exp(-Kc[(l + 1) * N + (lane - N)] * (taus[l + 2] - taus[l + 1]));
+        g.sync();
+        if (lane < N2) E[lane] = e_new;
+        g.sync();
+
+        // ---- carry rows: their C_{l} part is what used to be the C_{l+1} part ----
+        if (l > 0 && active) {
+#pragma unroll
+            for (int c = 0; c < N2; ++c) {
+                a[c] = a[N2 + c];
+                a[N2 + c] = 0.0;
+            }
+        }
+        // ---- freed lanes take the new rows ----
+        const unsigned freed = (__ballot_sync(g.mask, myj >= 0) >> gbase) & ((LS == 32) ? 0xffffffffu : ((1u << (LS & 31)) - 1u));
+        if (myj >= 0) {
+            const int idx = __popc(freed & ((1u << lane) - 1u));
+            myj = -1;
+            if (!last) {  // continuity row `idx` of interface l  (_solve_for_coeffs.py:317-323, :242-245, :184-205)
+                const double* g0 = Grow(l, idx, 0);
+                const double* g1 = Grow(l, idx, 1);
+                const double* h0 = Grow(l + 1, idx, 0);
+                const double* h1 = Grow(l + 1, idx, 1);
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    a[c] = g0[c] * E[c];
+                    a[N + c] = g1[c];
+                    a[N2 + c] = -h0[c];
+                    a[3 * N + c] = -h1[c] * E[N + c];
+                }
+                double v = 0.0;
+                if (beam) v = (Bc[(l + 1) * N2 + idx] - Bc[l * N2 + idx]) * exp(-taus[l + 1] / mu0);
+                if (dthc)
+                    v += pd_thermal_at(dthc + (long)(l + 1) * A.Ns * N2, A.Ns, N2, idx, taus[l + 1]) -
+                         pd_thermal_at(dthc + (long)l * A.Ns * N2, A.Ns, N2, idx, taus[l + 1]);
+                a[RC] = v;
+                active = hasrow = true;
+            } else if (idx < N) {  // bottom boundary row `idx`  (:163, :208-232, :248-254, :289-293)
+                const double* g0 = Grow(l, idx, 0);
+                const double* g1 = Grow(l, idx, 1);
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    double v0 = g0[c], v1 = g1[c];
+                    if (has_bdrf)
+                        for (int j = 0; j < N; ++j) {
+                            v0 = fma(-R[idx * N + j], Grow(l, N + j, 0)[c], v0);
+                            v1 = fma(-R[idx * N + j], Grow(l, N + j, 1)[c], v1);
+                        }
+                    a[c] = v0 * E[c];
+                    a[N + c] = v1;
+                    a[N2 + c] = 0.0;
+                    a[3 * N + c] = 0.0;
+                }
+                double v = have_b ? bpos[idx] : 0.0;
+                if (dthc) {
+                    const double* dl = dthc + (long)l * A.Ns * N2;
+                    v -= pd_thermal_at(dl, A.Ns, N2, idx, taus[L]);
+                    if (has_bdrf)
+                        for (int j = 0; j < N; ++j) v = fma(R[idx * N + j], pd_thermal_at(dl, A.Ns, N2, N + j, taus[L]), v);
+                }
+                if (beam) {
+                    double s = -Bc[l * N2 + idx];
+                    if (has_bdrf) {
+                        const double* q0 = A.bdrf_q0 + ((A.bdrf_percol ? (long)b * A.NBDRF : 0) + m) * N;
+                        s += (mu0 * I0 / PD_PI) * q0[idx];
+                        for (int j = 0; j < N; ++j) s = fma(R[idx * N + j], Bc[l * N2 + N + j], s);
+                    }
+                    v = fma(s, exp(-taus[L] / mu0), v);
+                }
+                a[RC] = v;
+                active = hasrow = true;
+            } else {  // last stage needs only N new rows
+#pragma unroll
+                for (int c = 0; c < NCOL; ++c) a[c] = 0.0;
+                active = hasrow = false;
+            }
+        }
+
+        // ---- Gauss-Jordan elimination of the 2N columns of C_l, partial pivoting over the rows in play ----
+        pd_static_for<0, N2>([&](auto JI) {
+            constexpr int j = decltype(JI)::value;
+            double* pb = buf + (j & 1) * LDB;
+            bool zero;
+            const int p = pd_group_argmax_slot<LS>(g.mask, fabs(a[j]), lane, active, zero);
+            if (zero) status |= PD_ST_ZERO_PIVOT;
+            if (lane == p) {  // publish the pivot row (columns j..4N, 16-byte chunks)
+                constexpr int c0 = j & ~1;
+#pragma unroll
+                for (int c = c0; c < NCOL; c += 2) {
+                    double2 v2;
+                    v2.x = a[c];
+                    v2.y = (c + 1 < NCOL) ? a[c + 1] : 0.0;
+                    *reinterpret_cast<double2*>(pb + c) = v2;
+                }
+            }
+            g.sync();
+            const double pinv = pd_fast_rcp(pb[j]);
+            double mneg = 0.0;
+            if (lane == p) {
+                active = false;
+                myj = j;
+                mypinv = pinv;
+            } else if (hasrow) {
+                mneg = -a[j] * pinv;
+            }
+            constexpr int c1 = (j + 1) & ~1;
+#pragma unroll
+            for (int c = c1; c < NCOL; c += 2) {
+                const double2 u2 = *reinterpret_cast<const double2*>(pb + c);
+                if (c > j) a[c] = fma(mneg, u2.x, a[c]);
+                if (c + 1 < NCOL) a[c + 1] = fma(mneg, u2.y, a[c + 1]);
+            }
+        });
+
+        if (!last) {
+            // pivot row of step r now holds row r of U11^-1 [U12 | y] up to its pivot: write [M_l | z_l]
+            if (myj >= 0) {
+                double* h = hist + (long)l * F::HIST_PER_LAYER + (long)myj * HROW;
+#pragma unroll
+                for (int c = 0; c < N2; ++c) h[c] = -a[N2 + c] * mypinv;
+                h[N2] = a[RC] * mypinv;
+                hasrow = false;
+            }
+        } else {
+            if (myj >= 0) xs[myj] = a[RC] * mypinv;
+        }
+    }
+    g.sync();
+
+    // ---- back sweep: x_l = z_l + M_l x_{l+1} ----
+    double* Cout = A.C + sys * L * N2;
+    if (lane < N2) Cout[(long)(L - 1) * N2 + lane] = xs[lane];
+    for (int l = L - 2; l >= 0; --l) {
+        const double* h = hist + (long)l * F::HIST_PER_LAYER;
+        double s = 0.0;
+        if (lane < N2) {
+            s = h[lane * HROW + N2];
+#pragma unroll
+            for (int c = 0; c < N2; ++c) s = fma(h[lane * HROW + c], xs[c], s);
+        }
+        g.sync();
+        if (lane < N2) {
+            xs[lane] = s;
+            Cout[(long)l * N2 + lane] = s;
+        }
+        g.sync();
+    }
+    if (status && lane == 0) atomicOr(A.status + b, status);
+}
+
+#endif  // __CUDACC__
