@@ -68,8 +68,8 @@ static bool use_reg(int N) {
     return true;
 }
 
-template <int N>
-__global__ void __launch_bounds__(128, 4) k_stage_b_reg(PdStageB a, double* hist, long hist_doubles) {
+template <int N, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_stage_b_reg(PdStageB a, double* hist, long hist_doubles) {
     extern __shared__ double smem[];
     constexpr int LS = 4 * N;
     constexpr int SD = (PdStageBRow<N>::SMEM_DOUBLES + 1) & ~1;
@@ -83,7 +83,15 @@ __global__ void __launch_bounds__(128, 4) k_stage_b_reg(PdStageB a, double* hist
     for (long s = slot; s < nsys; s += nslots) pd_stage_b_row<N, LS>(g, a, (int)(s / a.NF), (int)(s % a.NF), sm, h);
 }
 
-template <int N>
+static int reg_minb() {  // resident CTAs per SM the register-resident kernel is compiled for (tuning knob)
+    if (const char* e = getenv("PD_STAGE_B_MINB")) {
+        const int v = atoi(e);
+        if (v >= 3 && v <= 6) return v;
+    }
+    return 4;
+}
+
+template <int N, int MINB>
 static StageBPlan plan_reg(int B, int NF, int L) {
     StageBPlan p;
     constexpr int LS = 4 * N;
@@ -95,8 +103,8 @@ static StageBPlan plan_reg(int B, int NF, int L) {
     if (ctas_per_sm * p.wpb > 32) ctas_per_sm = 32 / p.wpb;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     int occ = 0;
-    if (cudaFuncSetAttribute(k_stage_b_reg<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stage_b_reg<N>, p.wpb * 32, p.smem) == cudaSuccess &&
+    if (cudaFuncSetAttribute(k_stage_b_reg<N, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stage_b_reg<N, MINB>, p.wpb * 32, p.smem) == cudaSuccess &&
         occ > 0) {
         if (occ < ctas_per_sm) ctas_per_sm = occ;
     } else {
@@ -111,12 +119,28 @@ static StageBPlan plan_reg(int B, int NF, int L) {
     return p;
 }
 
-template <int N>
+template <int N, int MINB>
 static int launch_reg(const PdStageB& a, const StageBPlan& pb, void* workspace, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(k_stage_b_reg<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb.smem);
+    cudaError_t e = cudaFuncSetAttribute(k_stage_b_reg<N, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb.smem);
     if (e != cudaSuccess) return (int)e;
-    k_stage_b_reg<N><<<pb.blocks, pb.wpb * 32, pb.smem, st>>>(a, (double*)workspace, pb.hist_doubles);
+    k_stage_b_reg<N, MINB><<<pb.blocks, pb.wpb * 32, pb.smem, st>>>(a, (double*)workspace, pb.hist_doubles);
     return (int)cudaGetLastError();
+}
+
+#define PD_REG_DISPATCH(N_, CALL)                      \
+    switch (reg_minb()) {                              \
+        case 3: { constexpr int MB = 3; return CALL; } \
+        case 5: { constexpr int MB = 5; return CALL; } \
+        case 6: { constexpr int MB = 6; return CALL; } \
+        default: { constexpr int MB = 4; return CALL; } \
+    }
+static StageBPlan plan_reg_any(int B, int NF, int N, int L) {
+    if (N == 4) { PD_REG_DISPATCH(4, (plan_reg<4, MB>(B, NF, L))) }
+    PD_REG_DISPATCH(8, (plan_reg<8, MB>(B, NF, L)))
+}
+static int launch_reg_any(const PdStageB& a, const StageBPlan& pb, void* workspace, cudaStream_t st) {
+    if (a.N == 4) { PD_REG_DISPATCH(4, (launch_reg<4, MB>(a, pb, workspace, st))) }
+    PD_REG_DISPATCH(8, (launch_reg<8, MB>(a, pb, workspace, st)))
 }
 
 template <int N>
@@ -148,7 +172,7 @@ static StageBPlan plan_fast(int B, int NF, int L, int ls) {
 }
 
 StageBPlan pd_plan_stage_b(int B, int NF, int N, int L) {
-    if (use_reg(N)) return N == 4 ? plan_reg<4>(B, NF, L) : plan_reg<8>(B, NF, L);
+    if (use_reg(N)) return plan_reg_any(B, NF, N, L);
     if (const int ls = fast_lanes(N)) {
         if (N == 4) return plan_fast<4>(B, NF, L, ls);
         if (N == 8) return plan_fast<8>(B, NF, L, ls);
@@ -193,7 +217,7 @@ int pd_launch_stage_b(const PdStageB& a, void* workspace, size_t workspace_bytes
     const StageBPlan pb = pd_plan_stage_b(a.B, a.NF, a.N, a.L);
     if (workspace_bytes < (size_t)pb.slots * pb.hist_doubles * 8 || !workspace) return -20;
     if (pb.smem > PD_SMEM_MAX_CTA) return -21;
-    if (use_reg(a.N)) return a.N == 4 ? launch_reg<4>(a, pb, workspace, st) : launch_reg<8>(a, pb, workspace, st);
+    if (use_reg(a.N)) return launch_reg_any(a, pb, workspace, st);
     if (const int ls = fast_lanes(a.N)) {
         const int key = a.N * 100 + ls;
         switch (key) {

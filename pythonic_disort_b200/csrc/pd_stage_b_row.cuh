@@ -198,37 +198,47 @@ __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, i
         }
 
         // ---- Gauss-Jordan elimination of the 2N columns of C_l, partial pivoting over the rows in play ----
+        // Software pipelining: the pivot search of step j+1 (two warp reductions) is issued right after
+        // column j+1 has been updated in step j, so its latency hides behind the rest of the row update; the
+        // pivot lane publishes 1/pivot with its row, so the other lanes do not wait for a reciprocal.
+        bool zero;
+        int p = pd_group_argmax_slot<LS>(g.mask, fabs(a[0]), lane, active, zero);
+        if (zero) status |= PD_ST_ZERO_PIVOT;
         pd_static_for<0, N2>([&](auto JI) {
             constexpr int j = decltype(JI)::value;
             double* pb = buf + (j & 1) * LDB;
-            bool zero;
-            const int p = pd_group_argmax_slot<LS>(g.mask, fabs(a[j]), lane, active, zero);
-            if (zero) status |= PD_ST_ZERO_PIVOT;
-            if (lane == p) {  // publish the pivot row (columns j..4N, 16-byte chunks)
+            const double myrcp = pd_fast_rcp(a[j]);
+            if (lane == p) {  // publish the pivot row (columns j..4N, 16-byte chunks) and 1/pivot
                 constexpr int c0 = j & ~1;
 #pragma unroll
                 for (int c = c0; c < NCOL; c += 2) {
                     double2 v2;
                     v2.x = a[c];
-                    v2.y = (c + 1 < NCOL) ? a[c + 1] : 0.0;
+                    v2.y = (c + 1 < NCOL) ? a[c + 1] : myrcp;
                     *reinterpret_cast<double2*>(pb + c) = v2;
                 }
             }
             g.sync();
-            const double pinv = pd_fast_rcp(pb[j]);
             double mneg = 0.0;
             if (lane == p) {
                 active = false;
                 myj = j;
-                mypinv = pinv;
+                mypinv = myrcp;
             } else if (hasrow) {
-                mneg = -a[j] * pinv;
+                mneg = -a[j] * pb[NCOL];
             }
-            constexpr int c1 = (j + 1) & ~1;
+            if constexpr (j + 1 < N2) {  // column j+1 first, then start looking for the next pivot
+                a[j + 1] = fma(mneg, pb[j + 1], a[j + 1]);
+                bool z2;
+                p = pd_group_argmax_slot<LS>(g.mask, fabs(a[j + 1]), lane, active, z2);
+                if (z2) status |= PD_ST_ZERO_PIVOT;
+            }
+            constexpr int cs = (j + 1 < N2) ? j + 2 : j + 1;  // first column still to update
+            constexpr int c1 = cs & ~1;
 #pragma unroll
             for (int c = c1; c < NCOL; c += 2) {
                 const double2 u2 = *reinterpret_cast<const double2*>(pb + c);
-                if (c > j) a[c] = fma(mneg, u2.x, a[c]);
+                if (c >= cs) a[c] = fma(mneg, u2.x, a[c]);
                 if (c + 1 < NCOL) a[c + 1] = fma(mneg, u2.y, a[c + 1]);
             }
         });
