@@ -160,8 +160,16 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     ncol = args.columns or wl["columns"]
-    chunk = min(args.chunk, ncol)
     only_flux = wl.get("only_flux", False)
+    if args.chunk > 0:
+        chunk = min(args.chunk, ncol)
+    else:  # columns per pydisort() call: keep the solved state (K, G, Bv, C) of one call under ~32 GB
+        shape = {"sw": (60, 8, 16), "lw": (60, 4, 1), "ha": (100, 16, 32)}[wl["ens"]]
+        nf = 1 if only_flux else shape[2]
+        per_col = nf * shape[0] * (2 * shape[1] ** 2 + 5 * shape[1]) * 8
+        chunk = max(1024, min(ncol, 65536, int(32e9 / per_col) // 1024 * 1024))
+        if wl["ens"] == "sw" and not only_flux:
+            chunk = min(chunk, 16384)
 
     # weak scaling: every rank owns its own `ncol` columns of the (unbounded) seeded ensemble
     ens = make_inputs(wl["ens"], ncol, rank * ncol, only_flux)
@@ -367,7 +375,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sw", choices=sorted(WORKLOADS))
     ap.add_argument("--columns", type=int, default=0, help="columns per GPU (default: the workload's full size)")
-    ap.add_argument("--chunk", type=int, default=16384, help="columns per pydisort() call")
+    ap.add_argument("--chunk", type=int, default=0, help="columns per pydisort() call (0 = sized from the workload)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
