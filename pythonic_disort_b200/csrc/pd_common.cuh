@@ -47,9 +47,19 @@ struct SubWarp {
 // padded leading dimension: odd, so that row- and column-wise lane access are both bank-conflict free
 PD_HD int pd_ld(int n) { return n | 1; }
 
+struct alignas(16) pd_d2 {  // two doubles moved with one 128-bit access
+    double x, y;
+};
+
+// 1/sqrt(x), x > 0 finite: hardware seed (MUFU.RSQ64H) + two Newton steps (about 1 ulp)
 PD_HD double pd_rsqrt(double x) {
 #if defined(__CUDA_ARCH__)
-    return rsqrt(x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    return y;
 #else
     return 1.0 / sqrt(x);
 #endif

@@ -174,44 +174,58 @@ PD_HD int pd_eig_real(const Grp& g, int n_rt, int ld_rt, double* H, double* Z, d
         g.sync();
         for (int i = l + lane; i <= hi; i += Grp::size) H[i * ld + i] -= sigma;
         g.sync();
-        // left rotations (lanes own columns): R = Q^T (H - sigma)
+        // left rotations (lanes own columns): R = Q^T (H - sigma).  Column k itself (r_k on the diagonal, zero
+        // below) is written after the loop, so one sync per rotation is enough.
         for (int k = l; k < hi; ++k) {
             const double x = H[k * ld + k], y = H[(k + 1) * ld + k];
-            double cr = 1.0, sr = 0.0;
+            double cr = 1.0, sr = 0.0, rr = x;
             if (y != 0.0) {
-                const double ri = pd_rsqrt(fma(x, x, y * y));
+                const double q2 = fma(x, x, y * y);
+                const double ri = pd_rsqrt(q2);
                 cr = x * ri;
                 sr = y * ri;
+                rr = q2 * ri;
             }
-            g.sync();  // everyone has read column k before its owner rewrites it
             if (lane == 0) {
-                cs[2 * k] = cr;
-                cs[2 * k + 1] = sr;
+                pd_d2 v;
+                v.x = cr;
+                v.y = sr;
+                *reinterpret_cast<pd_d2*>(cs + 2 * k) = v;
+                vec[k] = rr;
             }
-            for (int j = k + lane; j < n; j += Grp::size) {
+            for (int j = k + 1 + lane; j < n; j += Grp::size) {
                 const double t1 = H[k * ld + j], t2 = H[(k + 1) * ld + j];
                 H[k * ld + j] = fma(cr, t1, sr * t2);
-                H[(k + 1) * ld + j] = (j == k) ? 0.0 : fma(cr, t2, -sr * t1);
+                H[(k + 1) * ld + j] = fma(cr, t2, -sr * t1);
             }
             g.sync();
         }
-        // right rotations + shift restore (lanes own rows): H <- R Q + sigma, Z <- Z Q
+        for (int k = l + lane; k < hi; k += Grp::size) {
+            H[k * ld + k] = vec[k];
+            H[(k + 1) * ld + k] = 0.0;
+        }
+        g.sync();
+        // right rotations + shift restore (lanes own rows): H <- R Q + sigma, Z <- Z Q.  One pass over k for
+        // both matrices; the element shared by consecutive rotations stays in a register.
         for (int i = lane; i < n; i += Grp::size) {
-            if (i <= hi) {
-                for (int k = (i - 1 > l ? i - 1 : l); k < hi; ++k) {
-                    const double cr = cs[2 * k], sr = cs[2 * k + 1];
-                    const double t1 = H[i * ld + k], t2 = H[i * ld + (k + 1)];
-                    H[i * ld + k] = fma(cr, t1, sr * t2);
-                    H[i * ld + (k + 1)] = fma(cr, t2, -sr * t1);
-                }
-                if (i >= l) H[i * ld + i] += sigma;
-            }
+            const bool hrow = (i <= hi);
+            const int kh = (i - 1 > l) ? i - 1 : l;  // first rotation that touches row i of H
+            double zc = Z[i * ld + l];
+            double hc = hrow ? H[i * ld + kh] : 0.0;
             for (int k = l; k < hi; ++k) {
-                const double cr = cs[2 * k], sr = cs[2 * k + 1];
-                const double z1 = Z[i * ld + k], z2 = Z[i * ld + (k + 1)];
-                Z[i * ld + k] = fma(cr, z1, sr * z2);
-                Z[i * ld + (k + 1)] = fma(cr, z2, -sr * z1);
+                const pd_d2 rot = *reinterpret_cast<const pd_d2*>(cs + 2 * k);
+                const double zn = Z[i * ld + (k + 1)];
+                Z[i * ld + k] = fma(rot.x, zc, rot.y * zn);
+                zc = fma(rot.x, zn, -rot.y * zc);
+                if (hrow && k >= kh) {
+                    const double hn = H[i * ld + (k + 1)];
+                    const double v = fma(rot.x, hc, rot.y * hn);
+                    H[i * ld + k] = (k == i) ? v + sigma : v;
+                    hc = fma(rot.x, hn, -rot.y * hc);
+                }
             }
+            Z[i * ld + hi] = zc;
+            if (hrow) H[i * ld + hi] = (i == hi) ? hc + sigma : hc;
         }
         ++its;
         g.sync();

@@ -51,9 +51,9 @@ PD_HD void pd_stage_a_item(const Grp& g, const PdStageA& a, int b, int m, int l,
     double* A2 = A1 + n * ld;   // (alpha+beta)^
     double* H = A2 + n * ld;    // product -> Schur factor -> U^
     double* Z = H + n * ld;     // LU copy for the beam solve -> eigenvectors -> Gm
-    double* wr = Z + n * ld;    // [n] eigenvalues, then k
-    double* cs = wr + n;        // [2n]
-    double* vec = cs + 2 * n;   // [n]
+    double* cs = Z + n * ld;    // [2n] rotation pairs (16-byte aligned: 4 n ld is even)
+    double* wr = cs + 2 * n;    // [n] eigenvalues, then k
+    double* vec = wr + n;       // [n]
     double* x1 = vec + n;       // [n]
     double* x2 = x1 + n;        // [n]
     double* rhs = x2 + n;       // [n]
