@@ -78,7 +78,7 @@ int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const 
         if (e != cudaSuccess) return (int)e;
         PdStageA a;
         a.B = cfg->B; a.L = cfg->L; a.N = N; a.NLeg = cfg->NLeg; a.NF = cfg->NFourier; a.Ns = cfg->Nscoeffs;
-        a.beam = beam; a.iso = iso;
+        a.beam = beam; a.iso = iso; a.only_flagged = 0;
         a.omega_s = omega_s; a.wleg = wleg; a.s_s = s_s; a.colp = colp; a.pmu0 = pmu0; a.mu = mu_nodes; a.w = w_nodes;
         a.K = K; a.G = G; a.Bv = Bv; a.dth = dth; a.status = status;
         if (int rc = pd_launch_stage_a(a, ptab, pd_stream(stream))) return rc;

@@ -1,5 +1,8 @@
 // pd_kernel_a.cu -- stage A kernel: one lane group per (column, layer) item, one Fourier mode per blockIdx.y
+#include <stdlib.h>
+
 #include "pd_launch.h"
+#include "pd_stage_a_sym.cuh"
 
 template <int LANES, int NC>
 __global__ void k_stage_a(PdStageA a, const double* __restrict__ ptab, int items_per_cta, int item_doubles) {
@@ -20,7 +23,65 @@ __global__ void k_stage_a(PdStageA a, const double* __restrict__ ptab, int items
     pd_stage_a_item<SubWarp<LANES>, NC>(g, a, (int)(it / a.L), m, (int)(it % a.L), Q, sm);
 }
 
-int pd_launch_stage_a(const PdStageA& a, const double* ptab, cudaStream_t st) {
+// one thread per item, symmetric (Cholesky + Jacobi) path, N = 4 or 8
+#define PD_SYM_THREADS 128
+template <int N>
+__global__ void __launch_bounds__(PD_SYM_THREADS, (N <= 4) ? 4 : 2) k_stage_a_sym(PdStageA a, const double* __restrict__ ptab) {
+    extern __shared__ double smem[];
+    using P = PdSym<N>;
+    const int m = blockIdx.y, nm = a.NLeg - m;
+    double* Qs = smem;                                  // [nm][N]
+    double* QQ = Qs + ((nm * N + 1) & ~1);              // [nm][NP]
+    double* park = QQ + ((nm * P::NP + 1) & ~1);        // [PARK][threads]
+    for (int idx = threadIdx.x; idx < nm * N; idx += blockDim.x) {
+        const int i = idx % N;
+        Qs[idx] = ptab[((long)m * a.NLeg + m) * N + idx] * sqrt(a.w[i] / a.mu[i]);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nm * P::NP; idx += blockDim.x) {
+        const int t = idx / P::NP, e = idx - t * P::NP;
+        int i = 0, rem = e;  // unpack e -> (i, j), i <= j
+        while (rem >= N - i) {
+            rem -= N - i;
+            ++i;
+        }
+        QQ[idx] = Qs[t * N + i] * Qs[t * N + i + rem];
+    }
+    __syncthreads();
+    const long it = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= (long)a.B * a.L) return;
+    const int b = (int)(it / a.L), l = (int)(it % a.L);
+    const bool done = pd_stage_a_sym_item<N>(a, b, m, l, QQ, Qs, park + threadIdx.x, blockDim.x);
+    if (!done) a.K[(((long)b * a.NF + m) * a.L + l) * N] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
+template <int N>
+static int launch_sym(const PdStageA& a, const double* ptab, cudaStream_t st) {
+    using P = PdSym<N>;
+    const size_t smem = (size_t)(((a.NLeg * N + 1) & ~1) + ((a.NLeg * P::NP + 1) & ~1) + P::PARK * PD_SYM_THREADS) * 8;
+    cudaError_t e = cudaFuncSetAttribute(k_stage_a_sym<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const long items = (long)a.B * a.L;
+    dim3 grid((unsigned)((items + PD_SYM_THREADS - 1) / PD_SYM_THREADS), a.NF);
+    k_stage_a_sym<N><<<grid, PD_SYM_THREADS, smem, st>>>(a, ptab);
+    return (int)cudaGetLastError();
+}
+
+static bool use_sym(int N) {
+    if (N != 4 && N != 8) return false;
+    if (const char* e = getenv("PD_STAGE_A_GENERAL"))
+        if (e[0] == '1') return false;
+    return true;
+}
+
+int pd_launch_stage_a(const PdStageA& a_in, const double* ptab, cudaStream_t st) {
+    PdStageA a = a_in;
+    a.only_flagged = 0;
+    if (use_sym(a.N)) {  // symmetric fast path first; the general kernel then only redoes flagged items
+        const int rc = (a.N == 4) ? launch_sym<4>(a, ptab, st) : launch_sym<8>(a, ptab, st);
+        if (rc) return rc;
+        a.only_flagged = 1;
+    }
     const int N = a.N, lanes = pd_lanes_for(N);
     const int item_doubles = (pd_stage_a_item_doubles(N, a.NLeg) + 1) & ~1;
     const size_t qbytes = (size_t)((a.NLeg * N + 1) & ~1) * 8;

@@ -17,6 +17,7 @@
 struct PdStageA {
     int B, L, N, NLeg, NF, Ns;
     int beam, iso;
+    int only_flagged;       // recompute only items whose K[item][0] is NaN (fallback pass after the symmetric kernel)
     const double* omega_s;  // [B][L]
     const double* wleg;     // [B][L][NLeg]
     const double* s_s;      // [B][L][Ns]
@@ -70,6 +71,7 @@ PD_HD void pd_stage_a_item(const Grp& g, const PdStageA& a, int b, int m, int l,
     double* Bout = a.beam ? a.Bv + item * 2 * n : nullptr;
     const bool thermal = a.iso && m == 0;
     const bool beam = a.beam && a.colp[(long)b * PD_NCOLP + PD_COL_I0] > 0.0;  // per column (pydisort.py:215)
+    if (a.only_flagged && Kout[0] == Kout[0]) return;  // not NaN: already solved (group-uniform)
 
     bool active = false;  // _solve_for_gen_and_part_sols.py:119
     for (int t = 0; t < nm; ++t) active = active || (fabs((omega / 2) * wl[t]) > 1e-8);

@@ -1,0 +1,410 @@
+// pd_stage_a_sym.cuh -- stage A for N = 4 and 8: ONE THREAD per (column, mode, layer) item,
+// everything in registers, fixed control flow (production path for the shortwave / longwave
+// shapes; pd_stage_a.cuh + pd_linalg.cuh stay the general path and the fallback).
+//
+// In the similarity-scaled basis x^ = D x, D = diag(sqrt(w mu)), the reduced matrices are symmetric:
+//     X' = -(alpha - beta)^ = diag(1/mu) - sum_{l-m odd}  omega* (2l+1) g*_l Q_l Q_l^T
+//     S  = -(alpha + beta)^ = diag(1/mu) - sum_{l-m even} omega* (2l+1) g*_l Q_l Q_l^T
+// and for omega* < 1 both are positive definite, so the eigenproblem of
+// (alpha-beta)(alpha+beta) = X' S (_solve_for_gen_and_part_sols.py:179-183) becomes a symmetric one:
+//     S = L L^T (Cholesky),  T = L^T X' L,  T W = W diag(k^2),  W orthogonal,
+//     eigenvectors V^ = L^-T W,   U^ = (alpha+beta)^ V^ / k = -L W / k,   (V^)^-1 = W^T L^T.
+// T is diagonalised by cyclic Jacobi rotations: no data-dependent branches or indices, so 32 items
+// run in lock-step in one warp with all matrices in registers, and Jacobi delivers the small
+// eigenvalues (omega* -> 1) to high relative accuracy.  The particular solutions reuse the
+// decomposition instead of LU factorisations:
+//     beam    (:209-231): p^ = V^ diag(1/(1/mu0^2 - k^2)) W^T L^T r,  q^ = mu0 [(x1-x2) - L L^T p^]
+//     thermal (:201-205): G^-1 [1/mu; -1/mu] = [y; -y],  y = (U^)^-1 D/mu = -k * W^T L^-1 (D/mu)
+// If S is not numerically positive definite or Jacobi does not converge, the item is flagged
+// (K[item][0] = NaN) and the general Hessenberg-QR kernel recomputes it.
+#pragma once
+#include "pd_stage_a.cuh"
+
+#define PD_JACOBI_MAX_SWEEPS 12
+
+template <int N>
+struct PdSym {
+    static constexpr int NP = N * (N + 1) / 2;      // packed symmetric / triangular size
+    static constexpr int PARK = NP + N + 2 * N;     // per-thread parked doubles: L, 1/diag(L), r, x1-x2
+    PD_HD static constexpr int idx(int i, int j) {  // upper-packed index of (i, j), any order
+        return (i <= j) ? (i * N - i * (i - 1) / 2 + (j - i)) : (j * N - j * (j - 1) / 2 + (i - j));
+    }
+};
+
+// sm: per-thread parking area with stride `ps` between consecutive doubles of one thread
+// QQ: [nm][NP] products Q_t[i] Q_t[j] (i <= j), Qs: [nm][N] scaled Legendre table, both shared by the CTA
+// Returns true if the item is done, false if the general solver must recompute it.
+template <int N>
+PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const double* QQ, const double* Qs, double* sm,
+                               int ps) {
+    using P = PdSym<N>;
+    constexpr int NP = P::NP;
+    const int nm = a.NLeg - m;
+    const long item = ((long)b * a.NF + m) * a.L + l;
+    const double omega = a.omega_s[(long)b * a.L + l];
+    const double* wl = a.wleg + ((long)b * a.L + l) * a.NLeg + m;
+    double* Kout = a.K + item * N;
+    double* Gp_out = a.G + item * 2 * N * N;
+    double* Gm_out = Gp_out + N * N;
+    double* Bout = a.beam ? a.Bv + item * 2 * N : nullptr;
+    const bool thermal = a.iso && m == 0;
+    const bool beam = a.beam && a.colp[(long)b * PD_NCOLP + PD_COL_I0] > 0.0;
+
+    bool active = false;  // _solve_for_gen_and_part_sols.py:119
+    for (int t = 0; t < nm; ++t) active = active || (fabs((omega / 2) * wl[t]) > 1e-8);
+    if (!active) {  // shortcut (:162-168): G = [[0, I], [I, 0]], K = 1/mu, B = 0
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            Kout[i] = 1.0 / a.mu[i];
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                Gp_out[i * N + j] = 0.0;
+                Gm_out[i * N + j] = (i == j) ? 1.0 : 0.0;
+            }
+            if (a.beam) {
+                Bout[i] = 0.0;
+                Bout[N + i] = 0.0;
+            }
+        }
+        if (thermal) {  // y = -1/mu, k = 1/mu:  top = b_q(+k)/mu, bottom = -b_q(-k)/mu
+            const double* sc = a.s_s + ((long)b * a.L + l) * a.Ns;
+            double* dout = a.dth + ((long)b * a.L + l) * a.Ns * 2 * N;
+            for (int q = 0; q < a.Ns; ++q)
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double kin = a.mu[i];
+                    double ratio = 1.0, pw = kin, bp = 0.0, bn = 0.0;
+                    for (int r = q; r < a.Ns; ++r) {
+                        if (r > q) {
+                            ratio *= (double)r;
+                            pw *= kin;
+                        }
+                        bp = fma(sc[r] * ratio, pw, bp);
+                        bn = fma(sc[r] * ratio, ((r - q) & 1) ? pw : -pw, bn);
+                    }
+                    dout[q * 2 * N + i] = bp / a.mu[i];
+                    dout[q * 2 * N + N + i] = -bn / a.mu[i];
+                }
+        }
+        return true;
+    }
+
+    double* Lp = sm;                   // [NP] Cholesky factor, packed: L(i,j), i >= j, at idx(j,i)
+    double* Li = sm + (long)NP * ps;   // [N] 1 / L(i,i)
+    double* rp = Li + (long)N * ps;    // [N] beam right-hand side r
+    double* xd = rp + (long)N * ps;    // [N] x1 - x2
+
+    // ---- X' and S (packed symmetric), beam source vectors ----
+    double Xp[NP], S[NP];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = i; j < N; ++j) {
+            const double dg = (i == j) ? 1.0 / a.mu[i] : 0.0;
+            Xp[P::idx(i, j)] = dg;
+            S[P::idx(i, j)] = dg;
+        }
+    double x1[N], x2[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) x1[i] = x2[i] = 0.0;
+    const double mu0 = a.colp[(long)b * PD_NCOLP + PD_COL_MU0];
+    const double fac = beam ? a.colp[(long)b * PD_NCOLP + PD_COL_I0] / (4.0 * PD_PI) * ((m == 0) ? 1.0 : 2.0) : 0.0;
+    const double* pm0 = a.pmu0 + ((long)b * a.NF + m) * a.NLeg + m;
+    for (int t = 0; t < nm; ++t) {
+        const double c = omega * wl[t];
+        const double* qq = QQ + t * NP;
+        if (t & 1) {
+#pragma unroll
+            for (int e = 0; e < NP; ++e) Xp[e] = fma(-c, qq[e], Xp[e]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < NP; ++e) S[e] = fma(-c, qq[e], S[e]);
+        }
+        if (beam) {
+            const double cb = fac * c * pm0[t];
+            const double* q = Qs + t * N;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double v = cb * q[i];
+                x1[i] += v;
+                x2[i] += (t & 1) ? v : -v;  // x2 = -(M^-1 X-)^
+            }
+        }
+    }
+    if (beam) {  // r = (x1 + x2)/mu0 + (alpha-beta)^ (x1 - x2) = (x1 + x2)/mu0 - X' (x1 - x2)
+        double d[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) d[i] = x1[i] - x2[i];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double s = (x1[i] + x2[i]) / mu0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) s = fma(-Xp[P::idx(i, j)], d[j], s);
+            rp[(long)i * ps] = s;
+            xd[(long)i * ps] = d[i];
+        }
+    }
+
+    // ---- Cholesky S = L L^T (in place), parked in shared memory ----
+    bool ok = true;
+    double linv[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double d = S[P::idx(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d = fma(-S[P::idx(k, j)], S[P::idx(k, j)], d);  // L(j,k) lives at idx(k,j)
+        ok = ok && (d > 0.0);
+        const double ri = pd_rsqrt(d > 0.0 ? d : 1.0);
+        linv[j] = ri;
+        S[P::idx(j, j)] = d * ri;
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) {
+            double s = S[P::idx(j, i)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s = fma(-S[P::idx(k, i)], S[P::idx(k, j)], s);
+            S[P::idx(j, i)] = s * ri;  // L(i,j)
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < NP; ++e) Lp[(long)e * ps] = S[e];
+#pragma unroll
+    for (int j = 0; j < N; ++j) Li[(long)j * ps] = linv[j];
+#define PD_L(i, j) Lp[(long)P::idx(j, i) * ps] /* L(i,j), i >= j */
+
+    // ---- T = L^T X' L (packed symmetric); L is read back from its parking place to keep registers free ----
+    double T[NP];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double p[N];  // column j of X' L
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = j; c < N; ++c) s = fma(Xp[P::idx(r, c)], PD_L(c, j), s);
+            p[r] = s;
+        }
+#pragma unroll
+        for (int i = 0; i <= j; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int r = i; r < N; ++r) s = fma(PD_L(r, i), p[r], s);
+            T[P::idx(i, j)] = s;
+        }
+    }
+
+    // ---- cyclic Jacobi: T -> diag(k^2), W accumulates the rotations ----
+    double W[N * N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) W[i * N + j] = (i == j) ? 1.0 : 0.0;
+    bool converged = false;
+    for (int sweep = 0; sweep < PD_JACOBI_MAX_SWEEPS; ++sweep) {
+        double off = 0.0, diag = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            diag += fabs(T[P::idx(i, i)]);
+#pragma unroll
+            for (int j = i + 1; j < N; ++j) off += fabs(T[P::idx(i, j)]);
+        }
+        converged = (off <= 1e-17 * diag);
+#if defined(__CUDA_ARCH__)
+        if (__all_sync(__activemask(), converged || !ok)) break;
+#else
+        if (converged || !ok) break;
+#endif
+#pragma unroll
+        for (int p = 0; p < N - 1; ++p)
+#pragma unroll
+            for (int q = p + 1; q < N; ++q) {
+                const double apq = T[P::idx(p, q)], app = T[P::idx(p, p)], aqq = T[P::idx(q, q)];
+                // rotation that annihilates T(p,q); identity if it is already negligible
+                // (an item that has converged is frozen, so its result does not depend on its warp neighbours)
+                const bool tiny = converged || fabs(apq) <= 1e-300 || fabs(apq) <= 1e-18 * sqrt(fabs(app * aqq));
+                const double theta = (aqq - app) / (2.0 * (tiny ? 1.0 : apq));
+                const double tt = 1.0 / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+                const double tn = tiny ? 0.0 : ((theta >= 0.0) ? tt : -tt);
+                const double c = pd_rsqrt(fma(tn, tn, 1.0)), s = tn * c;
+                T[P::idx(p, p)] = fma(-tn, apq, app);
+                T[P::idx(q, q)] = fma(tn, apq, aqq);
+                T[P::idx(p, q)] = tiny ? apq : 0.0;
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    if (r != p && r != q) {
+                        const double trp = T[P::idx(r, p)], trq = T[P::idx(r, q)];
+                        T[P::idx(r, p)] = fma(c, trp, -s * trq);
+                        T[P::idx(r, q)] = fma(s, trp, c * trq);
+                    }
+                    const double wp = W[r * N + p], wq = W[r * N + q];
+                    W[r * N + p] = fma(c, wp, -s * wq);
+                    W[r * N + q] = fma(s, wp, c * wq);
+                }
+            }
+    }
+    double k[N], kinv[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const double lam = T[P::idx(j, j)];
+        ok = ok && (lam > 0.0);
+        kinv[j] = pd_rsqrt(lam > 0.0 ? lam : 1.0);
+        k[j] = lam * kinv[j];
+    }
+    if (!(ok && converged)) return false;
+
+    // ---- K, G blocks:  V^ = L^-T W,  U^ = -L W / k;  Gp = (V^ + U^)/(2 D),  Gm = (V^ - U^)/(2 D) ----
+    double dinv[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        dinv[i] = 0.5 * pd_rsqrt(a.w[i] * a.mu[i]);
+        Kout[i] = k[i];
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double v[N], u[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) {  // u = -(L w) / k_j
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c <= r; ++c) s = fma(PD_L(r, c), W[c * N + j], s);
+            u[r] = -s * kinv[j];
+        }
+#pragma unroll
+        for (int r = N - 1; r >= 0; --r) {  // L^T v = w
+            double s = W[r * N + j];
+#pragma unroll
+            for (int c = r + 1; c < N; ++c) s = fma(-PD_L(c, r), v[c], s);
+            v[r] = s * Li[(long)r * ps];
+        }
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            Gp_out[r * N + j] = (v[r] + u[r]) * dinv[r];
+            Gm_out[r * N + j] = (v[r] - u[r]) * dinv[r];
+        }
+    }
+
+    // helper products with the factors:  V^ x = L^-T (W x),  U^ x = -L (W (x / k))
+    auto apply_V = [&](const double* x, double* out) {
+        double y[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < N; ++c) s = fma(W[r * N + c], x[c], s);
+            y[r] = s;
+        }
+#pragma unroll
+        for (int r = N - 1; r >= 0; --r) {
+            double s = y[r];
+#pragma unroll
+            for (int c = r + 1; c < N; ++c) s = fma(-PD_L(c, r), out[c], s);
+            out[r] = s * Li[(long)r * ps];
+        }
+    };
+    auto apply_U = [&](const double* x, double* out) {
+        double y[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < N; ++c) s = fma(W[r * N + c], x[c] * kinv[c], s);
+            y[r] = s;
+        }
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c <= r; ++c) s = fma(PD_L(r, c), y[c], s);
+            out[r] = -s;
+        }
+    };
+
+    if (a.beam && !beam) {
+#pragma unroll
+        for (int i = 0; i < 2 * N; ++i) Bout[i] = 0.0;
+    }
+    if (beam) {
+        double z[N], cvec[N], ph[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) {  // z = L^T r
+            double s = 0.0;
+#pragma unroll
+            for (int c = r; c < N; ++c) s = fma(PD_L(c, r), rp[(long)c * ps], s);
+            z[r] = s;
+        }
+        const double m2 = 1.0 / (mu0 * mu0);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {  // c = diag(1/(1/mu0^2 - k^2)) W^T z
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < N; ++r) s = fma(W[r * N + j], z[r], s);
+            cvec[j] = s / (m2 - k[j] * k[j]);
+        }
+        apply_V(cvec, ph);  // p^ = V^ c
+        // q^ = mu0 [ (x1 - x2) - L L^T p^ ]
+        double lt[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = r; c < N; ++c) s = fma(PD_L(c, r), ph[c], s);
+            lt[r] = s;
+        }
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c <= r; ++c) s = fma(PD_L(r, c), lt[c], s);
+            const double qh = mu0 * (xd[(long)r * ps] - s);
+            Bout[r] = (ph[r] + qh) * dinv[r];       // dinv carries the factor 1/2
+            Bout[N + r] = (ph[r] - qh) * dinv[r];
+        }
+    }
+
+    if (thermal) {
+        // y = -k * W^T L^-1 (D / mu),  D_i / mu_i = sqrt(w_i / mu_i)
+        double f[N], y1[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) {  // forward substitution L f = D/mu
+            double s = sqrt(a.w[r] / a.mu[r]);
+#pragma unroll
+            for (int c = 0; c < r; ++c) s = fma(-PD_L(r, c), f[c], s);
+            f[r] = s * Li[(long)r * ps];
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < N; ++r) s = fma(W[r * N + j], f[r], s);
+            y1[j] = -k[j] * s;
+        }
+        const double* sc = a.s_s + ((long)b * a.L + l) * a.Ns;
+        double* dout = a.dth + ((long)b * a.L + l) * a.Ns * 2 * N;
+        for (int q = 0; q < a.Ns; ++q) {
+            double dm[N], sp[N];  // t- - t+ and t- + t+  (t-+ = b_q(-+k) y1)
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                double ratio = 1.0, pw = kinv[j], bp = 0.0, bn = 0.0;
+                for (int r = q; r < a.Ns; ++r) {
+                    if (r > q) {
+                        ratio *= (double)r;
+                        pw *= kinv[j];
+                    }
+                    bp = fma(sc[r] * ratio, pw, bp);
+                    bn = fma(sc[r] * ratio, ((r - q) & 1) ? pw : -pw, bn);
+                }
+                dm[j] = (bn - bp) * y1[j];
+                sp[j] = (bn + bp) * y1[j];
+            }
+            double vv[N], uu[N];
+            apply_V(dm, vv);
+            apply_U(sp, uu);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                dout[q * 2 * N + i] = (vv[i] + uu[i]) * dinv[i];      // Gp t- - Gm t+
+                dout[q * 2 * N + N + i] = (vv[i] - uu[i]) * dinv[i];  // Gm t- - Gp t+
+            }
+        }
+    }
+#undef PD_L
+    return true;
+}

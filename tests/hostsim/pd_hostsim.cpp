@@ -12,12 +12,16 @@
 #include "../../pythonic_disort_b200/csrc/pd_eval.cuh"
 #include "../../pythonic_disort_b200/csrc/pd_prologue.cuh"
 #include "../../pythonic_disort_b200/csrc/pd_stage_a.cuh"
+#include "../../pythonic_disort_b200/csrc/pd_stage_a_sym.cuh"
 #include "../../pythonic_disort_b200/csrc/pd_stage_b.cuh"
 
 extern "C" {
 
 int pd_abi_version(void) { return PD_ABI_VERSION; }
 int pd_is_hostsim(void) { return 1; }
+static long g_sym_done = 0, g_general = 0;
+long pd_hostsim_count(int which) { return which ? g_general : g_sym_done; }
+void pd_hostsim_reset(void) { g_sym_done = g_general = 0; }
 
 size_t pd_workspace_bytes(const pd_config* cfg) {
     return (size_t)pd_stage_b_history_doubles(cfg->NQuad / 2, cfg->L) * 8;
@@ -53,7 +57,7 @@ int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const 
     a.B = cfg->B; a.L = cfg->L; a.N = N; a.NLeg = cfg->NLeg; a.NF = cfg->NFourier; a.Ns = cfg->Nscoeffs;
     a.beam = (cfg->flags & PD_FLAG_BEAM) != 0; a.iso = (cfg->flags & PD_FLAG_ISO) != 0;
     a.omega_s = omega_s; a.wleg = wleg; a.s_s = s_s; a.colp = colp; a.pmu0 = pmu0; a.mu = mu_nodes; a.w = w_nodes;
-    a.K = K; a.G = G; a.Bv = Bv; a.dth = dth; a.status = status;
+    a.K = K; a.G = G; a.Bv = Bv; a.dth = dth; a.status = status; a.only_flagged = 0;
     SerialGroup g;
     double* sm = (double*)malloc(sizeof(double) * (pd_stage_a_item_doubles(N, cfg->NLeg) + 16));
     double* Q = (double*)malloc(sizeof(double) * cfg->NLeg * N);
@@ -61,8 +65,28 @@ int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const 
         const int nm = cfg->NLeg - m;
         for (int idx = 0; idx < nm * N; ++idx)
             Q[idx] = ptab[((long)m * cfg->NLeg + m) * N + idx] * sqrt(w_nodes[idx % N] / mu_nodes[idx % N]);
+        // same dispatch as pd_launch_stage_a: symmetric one-thread-per-item path for N = 4, 8 (unless
+        // PD_STAGE_A_GENERAL=1), general Hessenberg-QR path otherwise and for flagged items
+        const bool sym = (N == 4 || N == 8) && !(getenv("PD_STAGE_A_GENERAL") && getenv("PD_STAGE_A_GENERAL")[0] == '1');
+        const int NPk = N * (N + 1) / 2;
+        double* QQ = (double*)malloc(sizeof(double) * (nm * NPk + 1));
+        double* park = (double*)malloc(sizeof(double) * (NPk + 3 * N + 1));
+        for (int t = 0; t < nm && sym; ++t) {
+            int e = 0;
+            for (int i = 0; i < N; ++i)
+                for (int j = i; j < N; ++j) QQ[t * NPk + e++] = Q[t * N + i] * Q[t * N + j];
+        }
         for (int b = 0; b < cfg->B; ++b)
-            for (int l = 0; l < cfg->L; ++l) pd_stage_a_item(g, a, b, m, l, Q, sm);
+            for (int l = 0; l < cfg->L; ++l) {
+                bool done = false;
+                if (sym && N == 4) done = pd_stage_a_sym_item<4>(a, b, m, l, QQ, Q, park, 1);
+                if (sym && N == 8) done = pd_stage_a_sym_item<8>(a, b, m, l, QQ, Q, park, 1);
+                if (done) ++g_sym_done;
+                else ++g_general;
+                if (!done) pd_stage_a_item(g, a, b, m, l, Q, sm);
+            }
+        free(QQ);
+        free(park);
     }
     free(sm);
     free(Q);

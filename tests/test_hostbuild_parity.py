@@ -33,3 +33,32 @@ def test_stamnes_criteria(name):
 @pytest.mark.parametrize("name", ["sw", "lw", "ha", "tp9c16"])
 def test_ensembles(name):
     parity_suite.check_ensemble_vs_golden(pd.pydisort, name)
+
+
+def _counts(lib):
+    import ctypes
+    lib.pd_hostsim_count.restype = ctypes.c_long
+    return lib.pd_hostsim_count(0), lib.pd_hostsim_count(1)
+
+
+def test_symmetric_eigen_path_covers_the_production_shapes_and_matches_the_general_path(monkeypatch):
+    """N = 4 / 8 items go through the Cholesky + Jacobi path (no fallbacks on the ensembles);
+    forcing the general Hessenberg-QR path gives the same answers."""
+    import warnings
+
+    from pythonic_disort_b200 import api, synthetic
+    lib = api._test_backend[0]
+    for name, ncol in (("sw", 3), ("lw", 6)):
+        ens = synthetic.make(name, ncol)
+        lib.pd_hostsim_reset()
+        fast = parity_suite.run_batched(pd.pydisort, ens)
+        sym, general = _counts(lib)
+        assert sym > 0 and general == 0, (name, sym, general)
+        monkeypatch.setenv("PD_STAGE_A_GENERAL", "1")
+        lib.pd_hostsim_reset()
+        slow = parity_suite.run_batched(pd.pydisort, ens)
+        assert _counts(lib)[0] == 0
+        monkeypatch.delenv("PD_STAGE_A_GENERAL")
+        for key in fast:
+            scale = np.max(np.abs(slow[key]))
+            assert np.max(np.abs(fast[key] - slow[key])) <= 1e-11 * scale, (name, key)
