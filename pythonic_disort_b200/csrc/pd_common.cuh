@@ -47,6 +47,19 @@ struct SubWarp {
 // padded leading dimension: odd, so that row- and column-wise lane access are both bank-conflict free
 PD_HD int pd_ld(int n) { return n | 1; }
 
+// 1/x to within about an ulp: hardware seed (MUFU.RCP64H) + two Newton steps, no slow path
+PD_HD double pd_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+
 struct alignas(16) pd_d2 {  // two doubles moved with one 128-bit access
     double x, y;
 };

@@ -219,11 +219,14 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
             for (int q = p + 1; q < N; ++q) {
                 const double apq = T[P::idx(p, q)], app = T[P::idx(p, p)], aqq = T[P::idx(q, q)];
                 // rotation that annihilates T(p,q); identity if it is already negligible
+                // t = tan(rotation angle) = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq),
+                // written without the division by apq:  t = sgn(d) 2 apq / (|d| + sqrt(d^2 + 4 apq^2)).
                 // (an item that has converged is frozen, so its result does not depend on its warp neighbours)
-                const bool tiny = converged || fabs(apq) <= 1e-300 || fabs(apq) <= 1e-18 * sqrt(fabs(app * aqq));
-                const double theta = (aqq - app) / (2.0 * (tiny ? 1.0 : apq));
-                const double tt = 1.0 / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
-                const double tn = tiny ? 0.0 : ((theta >= 0.0) ? tt : -tt);
+                const bool tiny = converged || (apq * apq <= 1e-36 * fabs(app * aqq));
+                const double d = aqq - app, a2 = 2.0 * apq;
+                const double h = fma(d, d, a2 * a2);
+                const double den = fabs(d) + h * pd_rsqrt(h > 0.0 ? h : 1.0);
+                const double tn = tiny ? 0.0 : ((d >= 0.0) ? a2 : -a2) * pd_rcp(den > 0.0 ? den : 1.0);
                 const double c = pd_rsqrt(fma(tn, tn, 1.0)), s = tn * c;
                 T[P::idx(p, p)] = fma(-tn, apq, app);
                 T[P::idx(q, q)] = fma(tn, apq, aqq);
