@@ -143,11 +143,17 @@ __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, i
                 const double* h0 = Grow(l + 1, idx, 0);
                 const double* h1 = Grow(l + 1, idx, 1);
 #pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    a[c] = g0[c] * E[c];
-                    a[N + c] = g1[c];
-                    a[N2 + c] = -h0[c];
-                    a[3 * N + c] = -h1[c] * E[N + c];
+                for (int c = 0; c < N; c += 2) {  // rows of G are 16-byte aligned: 128-bit loads
+                    const pd_d2 v0 = *reinterpret_cast<const pd_d2*>(g0 + c), v1 = *reinterpret_cast<const pd_d2*>(g1 + c);
+                    const pd_d2 w0 = *reinterpret_cast<const pd_d2*>(h0 + c), w1 = *reinterpret_cast<const pd_d2*>(h1 + c);
+                    a[c] = v0.x * E[c];
+                    a[c + 1] = v0.y * E[c + 1];
+                    a[N + c] = v1.x;
+                    a[N + c + 1] = v1.y;
+                    a[N2 + c] = -w0.x;
+                    a[N2 + c + 1] = -w0.y;
+                    a[3 * N + c] = -w1.x * E[N + c];
+                    a[3 * N + c + 1] = -w1.y * E[N + c + 1];
                 }
                 double v = 0.0;
                 if (beam) v = (Bc[(l + 1) * N2 + idx] - Bc[l * N2 + idx]) * exp(-taus[l + 1] / mu0);
@@ -245,11 +251,12 @@ __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, i
 
         if (!last) {
             // pivot row of step r now holds row r of U11^-1 [U12 | y] up to its pivot: write [M_l | z_l]
+            // (history layout [column][row]: the 2N pivot lanes write 2N consecutive doubles per instruction)
             if (myj >= 0) {
-                double* h = hist + (long)l * F::HIST_PER_LAYER + (long)myj * HROW;
+                double* h = hist + (long)l * F::HIST_PER_LAYER + myj;
 #pragma unroll
-                for (int c = 0; c < N2; ++c) h[c] = -a[N2 + c] * mypinv;
-                h[N2] = a[RC] * mypinv;
+                for (int c = 0; c < N2; ++c) h[c * N2] = -a[N2 + c] * mypinv;
+                h[N2 * N2] = a[RC] * mypinv;
                 hasrow = false;
             }
         } else {
@@ -265,9 +272,9 @@ __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, i
         const double* h = hist + (long)l * F::HIST_PER_LAYER;
         double s = 0.0;
         if (lane < N2) {
-            s = h[lane * HROW + N2];
+            s = h[N2 * N2 + lane];
 #pragma unroll
-            for (int c = 0; c < N2; ++c) s = fma(h[lane * HROW + c], xs[c], s);
+            for (int c = 0; c < N2; ++c) s = fma(h[c * N2 + lane], xs[c], s);
         }
         g.sync();
         if (lane < N2) {
