@@ -241,11 +241,15 @@ __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, i
             }
             constexpr int cs = (j + 1 < N2) ? j + 2 : j + 1;  // first column still to update
             constexpr int c1 = cs & ~1;
+            constexpr int NPAIR = (NCOL - c1 + 1) / 2;
+            pd_d2 ur[NPAIR];  // fetch the whole published row first, then the FMAs: exposes one load latency per step
 #pragma unroll
-            for (int c = c1; c < NCOL; c += 2) {
-                const double2 u2 = *reinterpret_cast<const double2*>(pb + c);
-                if (c >= cs) a[c] = fma(mneg, u2.x, a[c]);
-                if (c + 1 < NCOL) a[c + 1] = fma(mneg, u2.y, a[c + 1]);
+            for (int q = 0; q < NPAIR; ++q) ur[q] = *reinterpret_cast<const pd_d2*>(pb + c1 + 2 * q);
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) {
+                const int c = c1 + 2 * q;
+                if (c >= cs) a[c] = fma(mneg, ur[q].x, a[c]);
+                if (c + 1 < NCOL) a[c + 1] = fma(mneg, ur[q].y, a[c + 1]);
             }
         });
 
