@@ -298,22 +298,33 @@ def run_gpu(args):
     dom = max(stage_flops, key=lambda k: per_kernel.get(k, 0.0))
     dom_ms = per_kernel[dom]
     achieved = stage_flops[dom] * B / (dom_ms * 1e-3) / 1e12
+    N = NQuad // 2
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    N = NQuad // 2
     # algorithmic bytes of the dominant kernel per column: what it must read and write once
     item = NF * cfgL
     bytes_k = {"solve_eigen": item * (NLeg + 1) * 8 + item * (2 * N * N + N + 2 * N) * 8,
                "solve_bc": item * (2 * N * N + N + 2 * N) * 8 + item * 2 * N * 8}[dom]
-    roofline = {"kernel": {"solve_eigen": "k_stage_a", "solve_bc": "k_stage_b"}[dom], "bound": "fp64",
+    fastN = N in (4, 8)
+    kname = {"solve_eigen": "k_stage_a_sym" if fastN else "k_stage_a",
+             "solve_bc": "k_stage_b_reg" if fastN else ("k_stage_b_fast" if N == 16 else "k_stage_b")}[dom]
+    # DRAM bytes per column of that kernel from the committed ncu capture (profiles/r1_traffic.json), if any
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        per_col = tr.get(args.workload, {}).get(kname)
+        traffic = per_col * B if per_col else None
+    except (OSError, ValueError):
+        pass
+    roofline = {"kernel": kname, "bound": "fp64",
                 "achieved": achieved, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak_tflops if fp64_peak_tflops > 0 else None,
                 "peak_source": "pd_fp64_probe DFMA micro-benchmark, measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                "traffic": None,
+                "traffic": traffic,
                 "hbm": {"achieved_gbs": bytes_k * B / (dom_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                         "algorithmic_bytes_per_column": bytes_k},

@@ -189,12 +189,13 @@ struct PdNT {
 };
 
 // sum_{l<nc} coef[l] P_l(x) by upward recurrence (coefficients already carry their (2l+1) weights)
-PD_HD double pd_legendre_series(const double* coef, int nc, double x) {
+// rinv[l] = 1/l (l >= 1): a table, because an FP64 division per term would dominate the series
+PD_HD double pd_legendre_series(const double* coef, int nc, double x, const double* rinv) {
     double p0 = 1.0, p1 = x;
     double s = coef[0];
     if (nc > 1) s = fma(coef[1], x, s);
     for (int l = 1; l + 1 < nc; ++l) {
-        const double p2 = ((2 * l + 1) * x * p1 - l * p0) / (l + 1);
+        const double p2 = ((2 * l + 1) * x * p1 - l * p0) * rinv[l + 1];
         s = fma(coef[l + 1], p2, s);
         p0 = p1;
         p1 = p2;
@@ -203,12 +204,12 @@ PD_HD double pd_legendre_series(const double* coef, int nc, double x) {
 }
 
 // sum_{l<nc} (2l+1) g[l] P_l(x) for unweighted phase-function moments, g[0] taken as 1 (pydisort.py:246-248)
-PD_HD double pd_legendre_series_raw(const double* gl, int nc, double x) {
+PD_HD double pd_legendre_series_raw(const double* gl, int nc, double x, const double* rinv) {
     double p0 = 1.0, p1 = x;
     double s = 1.0;
     if (nc > 1) s = fma(3.0 * gl[1], x, s);
     for (int l = 1; l + 1 < nc; ++l) {
-        const double p2 = ((2 * l + 1) * x * p1 - l * p0) / (l + 1);
+        const double p2 = ((2 * l + 1) * x * p1 - l * p0) * rinv[l + 1];
         s = fma((2 * l + 3) * gl[l + 1], p2, s);
         p0 = p1;
         p1 = p2;
@@ -293,7 +294,7 @@ PD_HD void pd_ims_setup(const Grp& g, const PdEval& a, const PdNT& nt, int b, do
 // wall_l: the unweighted phase-function moments g_l[NLeg_all] of layer l.
 PD_HD double pd_nt_value(const PdEval& a, const PdNT& nt, int b, int i, int l, double tq, double ts, double phi,
                          const double* Rpos, const double* Rneg, const double* imsc, const double* imsv,
-                         const double* wall_l) {
+                         const double* wall_l, const double* rinv) {
     const int n = a.N, L = a.L;
     const double* cp = a.st.colp + (long)b * PD_NCOLP;
     const double mu0 = cp[PD_COL_MU0], I0 = cp[PD_COL_I0], phi0 = cp[PD_COL_PHI0];
@@ -307,8 +308,8 @@ PD_HD double pd_nt_value(const PdEval& a, const PdNT& nt, int b, int i, int l, d
     // cosine of the scattering angle between (mus, phi) and the beam (-mu0, phi0)
     const double nu = -mu0 * mus + sqrt(1.0 - mu0 * mu0) * sqrt(1.0 - mus * mus) * cphi;
     const double fl = nt.f[(long)b * L + l];
-    const double ptrue = pd_legendre_series_raw(wall_l, a.NLeg_all, nu);
-    const double ptrun = pd_legendre_series(nt.wleg + ((long)b * L + l) * a.NLeg, a.NLeg, nu);
+    const double ptrue = pd_legendre_series_raw(wall_l, a.NLeg_all, nu, rinv);
+    const double ptrun = pd_legendre_series(nt.wleg + ((long)b * L + l) * a.NLeg, a.NLeg, nu, rinv);
     const double Bsc = nt.omega_s[(long)b * L + l] * (I0 / (4.0 * PD_PI)) * (mu0 / (mu0 + mus)) * (ptrue / (1.0 - fl) - ptrun);
     const double sc = a.st.scale_tau[(long)b * L + l];
     const double ttop = taus[l], tbot = taus[l + 1];
@@ -333,7 +334,7 @@ PD_HD double pd_nt_value(const PdEval& a, const PdNT& nt, int b, int i, int l, d
             chi = ((mu0s - x * mu0s * (mu0s + tq)) * exp(-tq / mu0s) - mua * exp(-tq * mi)) / (mua * mu0s * x * x);
         else
             chi = ((tq - 1.0 / x) * exp(-tq / mu0s) + exp(-tq * mi) / x) / (mua * mu0s * x);
-        val += imsv[0] * pd_legendre_series(imsc, a.NLeg_all, nu2) * chi;
+        val += imsv[0] * pd_legendre_series(imsc, a.NLeg_all, nu2, rinv) * chi;
     }
     return val;
 }

@@ -63,7 +63,9 @@ __global__ void __launch_bounds__(256) k_nt(PdEval a, PdNT nt, const double* __r
     double* Rneg = Rpos + n * L;         // [n][L]
     double* imsc = Rneg + n * L;         // [NLeg_all]
     double* imsv = imsc + a.NLeg_all;    // [2]
+    double* rinv = imsv + 2;             // [NLeg_all + 1] 1/l
     if (a.st.colp[(long)b * PD_NCOLP + PD_COL_NT] == 0.0) return;  // gate of pydisort.py:375, column part
+    for (int i = threadIdx.x; i <= a.NLeg_all; i += blockDim.x) rinv[i] = (i > 0) ? 1.0 / (double)i : 0.0;
     if (threadIdx.x < 32) {
         SubWarp<32> g;
         if (L > 1) pd_tms_scans(g, a, b, Rpos, Rneg);
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(256) k_nt(PdEval a, PdNT nt, const double* __r
         const int l = pd_locate(a.st.tau + (long)b * L, L, tq);
         const double ts = pd_scaled_tau(a, b, l, tq);
         const double v = pd_nt_value(a, nt, b, i, l, tq, ts, phi_q[p], Rpos, Rneg, imsc, imsv,
-                                     nt.leg_all + ((long)b * L + l) * a.NLeg_all);
+                                     nt.leg_all + ((long)b * L + l) * a.NLeg_all, rinv);
         u[(((long)b * n2 + i) * a.ntau + t) * nphi + p] += resc * v;
     }
 }
@@ -151,7 +153,7 @@ int pd_eval_u(const pd_config* cfg, const pd_state* st, const double* tau_q, int
         if (!omega || !f || !leg_all || !omega_s || !wleg) return -32;
         PdNT p;
         p.omega = omega; p.f = f; p.leg_all = leg_all; p.omega_s = omega_s; p.wleg = wleg;
-        const size_t sm2 = (size_t)(2 * a.N * a.L + a.NLeg_all + 2) * 8;
+        const size_t sm2 = (size_t)(2 * a.N * a.L + 2 * a.NLeg_all + 4) * 8;
         if (sm2 > PD_SMEM_MAX_CTA) return -33;
         e = cudaFuncSetAttribute(k_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
         if (e != cudaSuccess) return (int)e;

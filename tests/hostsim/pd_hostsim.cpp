@@ -152,8 +152,9 @@ int pd_eval_u(const pd_config* cfg, const pd_state* st, const double* tau_q, int
     const int n = a.N, n2 = 2 * n, L = a.L;
     double* ev = (double*)malloc(sizeof(double) * (a.NF + 1) * n2);
     double* um = ev + n2;
-    double* scr = (double*)malloc(sizeof(double) * (2 * n * L + a.NLeg_all + 2));
-    double *Rpos = scr, *Rneg = scr + n * L, *imsc = scr + 2 * n * L, *imsv = imsc + a.NLeg_all;
+    double* scr = (double*)malloc(sizeof(double) * (2 * n * L + 2 * a.NLeg_all + 4));
+    double *Rpos = scr, *Rneg = scr + n * L, *imsc = scr + 2 * n * L, *imsv = imsc + a.NLeg_all, *rinv = imsv + 2;
+    for (int i = 0; i <= a.NLeg_all; ++i) rinv[i] = (i > 0) ? 1.0 / (double)i : 0.0;
     PdNT p;
     p.omega = omega; p.f = f; p.leg_all = leg_all; p.omega_s = omega_s; p.wleg = wleg;
     for (int b = 0; b < a.B; ++b) {
@@ -177,7 +178,7 @@ int pd_eval_u(const pd_config* cfg, const pd_state* st, const double* tau_q, int
                     double v = resc * s;
                     if (ntb)
                         v += resc * pd_nt_value(a, p, b, i, l, tq, ts, phi_q[q], Rpos, Rneg, imsc, imsv,
-                                                leg_all + ((long)b * L + l) * a.NLeg_all);
+                                                leg_all + ((long)b * L + l) * a.NLeg_all, rinv);
                     u[(((long)b * n2 + i) * ntau + t) * nphi + q] = v;
                 }
                 if (ulast) ulast[((long)b * n2 + i) * ntau + t] = um[(a.NF - 1) * n2 + i];
