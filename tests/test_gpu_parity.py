@@ -79,3 +79,56 @@ def test_cuda_tensor_inputs_give_cuda_outputs():
     assert Fp.is_cuda and Fp.shape == (16, 61)
     ref = parity_suite.run_batched(pd.pydisort, ens)
     np.testing.assert_allclose(Fp.cpu().numpy(), ref["flux_up"], rtol=1e-14)
+
+
+@pytest.mark.parametrize("env", [
+    {"PD_STAGE_A_GENERAL": "1"},                              # Hessenberg-QR eigen kernel instead of Cholesky+Jacobi
+    {"PD_STAGE_B_SMEM": "1"},                                 # shared-memory panel kernel instead of register rows
+    {"PD_STAGE_B_SMEM": "1", "PD_STAGE_B_LS": "16"},          # ... two systems per warp
+    {"PD_STAGE_B_GENERIC": "1", "PD_STAGE_A_GENERAL": "1"},   # size-generic kernels (what any other NQuad uses)
+])
+@pytest.mark.parametrize("name", ["sw", "lw", "tp9c"])
+def test_every_kernel_variant_meets_the_same_bar(monkeypatch, env, name):
+    """The production shapes have specialised kernels; the general ones are the fallback and serve every other
+    NQuad.  All of them must reproduce the reference."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    if name == "tp9c":
+        from oracle import disort_oracle
+        ens = synthetic.make(name, 2)
+        got = parity_suite.run_batched(pd.pydisort, ens)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = synthetic.run_reference_like(disort_oracle.pydisort, ens)
+        parity_suite.compare_fields(got, ref, 2, 1e-9, name)
+    else:
+        parity_suite.check_ensemble_vs_golden(pd.pydisort, name)
+
+
+def test_unphysical_phase_function_is_flagged_not_crashed():
+    """Moments that make the reduced matrices indefinite: the symmetric path must hand the item to the general
+    solver, which reports the non-positive k^2 (the reference returns NaN / complex garbage here)."""
+    leg = np.array([1.0, 0.99, -0.99, 0.99, -0.99])
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        out = pd.pydisort(np.array([0.5, 1.0]), np.array([0.999, 0.999]), 4, np.tile(leg, (2, 1)), 0.5, 1.0, 0.0)
+        out[1](0.3)
+    assert any("numerical trouble" in str(x.message) for x in w)
+
+
+def test_large_batch_properties():
+    """Full-size-style checks that need no oracle: energy conservation for a conservative-ish, black-surface,
+    beam-only ensemble slice (F_up(0) + F_down_total(tau_L) <= incident, >= 0) and monotone direct beam."""
+    ens = synthetic.make("sw", 2048, first=30000)
+    ens["kwargs"]["BDRF_Fourier_modes"] = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = pd.pydisort(*ens["args"], **ens["kwargs"])
+    t = ens["tau_eval"]
+    Fp = out[1](t)
+    Fd, Fdir = out[2](t)
+    incident = ens["args"][4] * ens["args"][5]  # mu0 * I0
+    assert np.all(Fp >= -1e-12) and np.all(Fd >= -1e-9) and np.all(np.diff(Fdir, axis=1) <= 0)
+    absorbed = incident - Fp[:, 0] - (Fd[:, -1] + Fdir[:, -1])
+    assert np.all(absorbed >= -1e-9 * incident) and np.all(absorbed <= incident)
+    np.testing.assert_allclose(Fdir[:, 0], incident, rtol=1e-14)
