@@ -68,7 +68,7 @@ static bool use_reg(int N) {
     return true;
 }
 
-template <int N, int MINB>
+template <int N, int MINB, bool SH>
 __global__ void __launch_bounds__(128, MINB) k_stage_b_reg(PdStageB a, double* hist, long hist_doubles) {
     extern __shared__ double smem[];
     constexpr int LS = 4 * N;
@@ -80,18 +80,18 @@ __global__ void __launch_bounds__(128, MINB) k_stage_b_reg(PdStageB a, double* h
     double* sm = smem + (long)gi * SD;
     double* h = hist + slot * hist_doubles;
     const long nsys = (long)a.B * a.NF;
-    for (long s = slot; s < nsys; s += nslots) pd_stage_b_row<N, LS>(g, a, (int)(s / a.NF), (int)(s % a.NF), sm, h);
+    for (long s = slot; s < nsys; s += nslots) pd_stage_b_row<N, LS, SH>(g, a, (int)(s / a.NF), (int)(s % a.NF), sm, h);
 }
 
 static int reg_minb() {  // resident CTAs per SM the register-resident kernel is compiled for (tuning knob)
     if (const char* e = getenv("PD_STAGE_B_MINB")) {
         const int v = atoi(e);
-        if (v >= 3 && v <= 6) return v;
+        if (v >= 3 && v <= 5) return v;
     }
     return 4;
 }
 
-template <int N, int MINB>
+template <int N, int MINB, bool SH>
 static StageBPlan plan_reg(int B, int NF, int L) {
     StageBPlan p;
     constexpr int LS = 4 * N;
@@ -103,8 +103,8 @@ static StageBPlan plan_reg(int B, int NF, int L) {
     if (ctas_per_sm * p.wpb > 32) ctas_per_sm = 32 / p.wpb;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     int occ = 0;
-    if (cudaFuncSetAttribute(k_stage_b_reg<N, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stage_b_reg<N, MINB>, p.wpb * 32, p.smem) == cudaSuccess &&
+    if (cudaFuncSetAttribute(k_stage_b_reg<N, MINB, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stage_b_reg<N, MINB, SH>, p.wpb * 32, p.smem) == cudaSuccess &&
         occ > 0) {
         if (occ < ctas_per_sm) ctas_per_sm = occ;
     } else {
@@ -119,28 +119,41 @@ static StageBPlan plan_reg(int B, int NF, int L) {
     return p;
 }
 
-template <int N, int MINB>
+template <int N, int MINB, bool SH>
 static int launch_reg(const PdStageB& a, const StageBPlan& pb, void* workspace, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(k_stage_b_reg<N, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb.smem);
+    cudaError_t e = cudaFuncSetAttribute(k_stage_b_reg<N, MINB, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb.smem);
     if (e != cudaSuccess) return (int)e;
-    k_stage_b_reg<N, MINB><<<pb.blocks, pb.wpb * 32, pb.smem, st>>>(a, (double*)workspace, pb.hist_doubles);
+    k_stage_b_reg<N, MINB, SH><<<pb.blocks, pb.wpb * 32, pb.smem, st>>>(a, (double*)workspace, pb.hist_doubles);
     return (int)cudaGetLastError();
 }
 
-#define PD_REG_DISPATCH(N_, CALL)                      \
-    switch (reg_minb()) {                              \
-        case 3: { constexpr int MB = 3; return CALL; } \
-        case 5: { constexpr int MB = 5; return CALL; } \
-        case 6: { constexpr int MB = 6; return CALL; } \
-        default: { constexpr int MB = 4; return CALL; } \
+static bool reg_shfl() {  // pivot-row broadcast by warp shuffles (default, ~5 % faster on B200) or via shared memory
+    const char* e = getenv("PD_STAGE_B_SHFL");
+    return !(e && e[0] == '0');
+}
+#define PD_REG_DISPATCH(N_, CALL)                                                  \
+    if (reg_shfl()) {                                                              \
+        constexpr bool SH = true;                                                  \
+        switch (reg_minb()) {                                                      \
+            case 3: { constexpr int MB = 3; return CALL; }                         \
+            case 5: { constexpr int MB = 5; return CALL; }                         \
+            default: { constexpr int MB = 4; return CALL; }                        \
+        }                                                                          \
+    } else {                                                                       \
+        constexpr bool SH = false;                                                 \
+        switch (reg_minb()) {                                                      \
+            case 3: { constexpr int MB = 3; return CALL; }                         \
+            case 5: { constexpr int MB = 5; return CALL; }                         \
+            default: { constexpr int MB = 4; return CALL; }                        \
+        }                                                                          \
     }
 static StageBPlan plan_reg_any(int B, int NF, int N, int L) {
-    if (N == 4) { PD_REG_DISPATCH(4, (plan_reg<4, MB>(B, NF, L))) }
-    PD_REG_DISPATCH(8, (plan_reg<8, MB>(B, NF, L)))
+    if (N == 4) { PD_REG_DISPATCH(4, (plan_reg<4, MB, SH>(B, NF, L))) }
+    PD_REG_DISPATCH(8, (plan_reg<8, MB, SH>(B, NF, L)))
 }
 static int launch_reg_any(const PdStageB& a, const StageBPlan& pb, void* workspace, cudaStream_t st) {
-    if (a.N == 4) { PD_REG_DISPATCH(4, (launch_reg<4, MB>(a, pb, workspace, st))) }
-    PD_REG_DISPATCH(8, (launch_reg<8, MB>(a, pb, workspace, st)))
+    if (a.N == 4) { PD_REG_DISPATCH(4, (launch_reg<4, MB, SH>(a, pb, workspace, st))) }
+    PD_REG_DISPATCH(8, (launch_reg<8, MB, SH>(a, pb, workspace, st)))
 }
 
 template <int N>

@@ -43,7 +43,7 @@ __device__ __forceinline__ void pd_static_for(F&& f) {
     }
 }
 
-template <int N, int LS>
+template <int N, int LS, bool SHFL_BCAST>
 __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, int m, double* sm, double* hist) {
     using F = PdStageBRow<N>;
     static_assert(LS >= 3 * N, "one lane per panel row");
@@ -124,6 +124,11 @@ __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, i
         if (lane < N2) E[lane] = e_new;
         g.sync();
 
+        // ---- pull the G block the NEXT stage will read (G_{l+2}) towards L1 while this stage computes ----
+#if defined(__CUDA_ARCH__)
+        if (l + 2 < L && lane * 16 < 2 * N * N)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(Gc + ((long)(l + 2) * 2) * N * N + lane * 16));
+#endif
         // ---- carry rows: their C_{l} part is what used to be the C_{l+1} part ----
         if (l > 0 && active) {
 #pragma unroll
@@ -212,6 +217,30 @@ __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, i
         if (zero) status |= PD_ST_ZERO_PIVOT;
         pd_static_for<0, N2>([&](auto JI) {
             constexpr int j = decltype(JI)::value;
+            if constexpr (SHFL_BCAST) {
+                // variant: the pivot row is broadcast with warp shuffles straight from the pivot lane's
+                // registers (no shared-memory round trip, no __syncwarp; twice the LSU-pipe instructions)
+                const double piv = __shfl_sync(g.mask, a[j], p, LS);
+                const double pinv = pd_rcp(piv);
+                double mneg = 0.0;
+                if (lane == p) {
+                    active = false;
+                    myj = j;
+                    mypinv = pinv;
+                } else if (hasrow) {
+                    mneg = -a[j] * pinv;
+                }
+                const int pcur = p;
+                if constexpr (j + 1 < N2) {
+                    a[j + 1] = fma(mneg, __shfl_sync(g.mask, a[j + 1], pcur, LS), a[j + 1]);
+                    bool z2;
+                    p = pd_group_argmax_slot<LS>(g.mask, fabs(a[j + 1]), lane, active, z2);
+                    if (z2) status |= PD_ST_ZERO_PIVOT;
+                }
+                constexpr int cs = (j + 1 < N2) ? j + 2 : j + 1;
+#pragma unroll
+                for (int c = cs; c < NCOL; ++c) a[c] = fma(mneg, __shfl_sync(g.mask, a[c], pcur, LS), a[c]);
+            } else {
             double* pb = buf + (j & 1) * LDB;
             const double myrcp = pd_fast_rcp(a[j]);
             if (lane == p) {  // publish the pivot row (columns j..4N, 16-byte chunks) and 1/pivot
@@ -250,6 +279,7 @@ __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, i
                 const int c = c1 + 2 * q;
                 if (c >= cs) a[c] = fma(mneg, ur[q].x, a[c]);
                 if (c + 1 < NCOL) a[c + 1] = fma(mneg, ur[q].y, a[c + 1]);
+            }
             }
         });
 
