@@ -43,16 +43,16 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
     const long item = ((long)b * a.NF + m) * a.L + l;
     const double omega = a.omega_s[(long)b * a.L + l];
     const double* wl = a.wleg + ((long)b * a.L + l) * a.NLeg + m;
-    double* Kout = a.K + item * N;
-    double* Gp_out = a.G + item * 2 * N * N;
-    double* Gm_out = Gp_out + N * N;
-    double* Bout = a.beam ? a.Bv + item * 2 * N : nullptr;
     const bool thermal = a.iso && m == 0;
     const bool beam = a.beam && a.colp[(long)b * PD_NCOLP + PD_COL_I0] > 0.0;
 
     bool active = false;  // _solve_for_gen_and_part_sols.py:119
     for (int t = 0; t < nm; ++t) active = active || (fabs((omega / 2) * wl[t]) > 1e-8);
     if (!active) {  // shortcut (:162-168): G = [[0, I], [I, 0]], K = 1/mu, B = 0
+        double* Kout = a.K + item * N;
+        double* Gp_out = a.G + item * 2 * N * N;
+        double* Gm_out = Gp_out + N * N;
+        double* Bout = a.beam ? a.Bv + item * 2 * N : nullptr;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             Kout[i] = 1.0 / a.mu[i];
@@ -255,6 +255,11 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
     if (!(ok && converged)) return false;
 
     // ---- K, G blocks:  V^ = L^-T W,  U^ = -L W / k;  Gp = (V^ + U^)/(2 D),  Gm = (V^ - U^)/(2 D) ----
+    // (output pointers are formed only now: nothing but `item` has to stay live across the Jacobi sweeps)
+    double* Kout = a.K + item * N;
+    double* Gp_out = a.G + item * 2 * N * N;
+    double* Gm_out = Gp_out + N * N;
+    double* Bout = a.beam ? a.Bv + item * 2 * N : nullptr;
     double dinv[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -286,7 +291,7 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
     }
 
     // helper products with the factors:  V^ x = L^-T (W x),  U^ x = -L (W (x / k))
-    auto apply_V = [&](const double* x, double* out) {
+    auto apply_V = [&](const double (&x)[N], double (&out)[N]) {
         double y[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) {
@@ -303,7 +308,7 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
             out[r] = s * Li[(long)r * ps];
         }
     };
-    auto apply_U = [&](const double* x, double* out) {
+    auto apply_U = [&](const double (&x)[N], double (&out)[N]) {
         double y[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) {
@@ -334,7 +339,8 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
             for (int c = r; c < N; ++c) s = fma(PD_L(c, r), rp[(long)c * ps], s);
             z[r] = s;
         }
-        const double m2 = 1.0 / (mu0 * mu0);
+        const double mu0b = a.colp[(long)b * PD_NCOLP + PD_COL_MU0];
+        const double m2 = 1.0 / (mu0b * mu0b);
 #pragma unroll
         for (int j = 0; j < N; ++j) {  // c = diag(1/(1/mu0^2 - k^2)) W^T z
             double s = 0.0;
@@ -357,7 +363,7 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
             double s = 0.0;
 #pragma unroll
             for (int c = 0; c <= r; ++c) s = fma(PD_L(r, c), lt[c], s);
-            const double qh = mu0 * (xd[(long)r * ps] - s);
+            const double qh = mu0b * (xd[(long)r * ps] - s);
             Bout[r] = (ph[r] + qh) * dinv[r];       // dinv carries the factor 1/2
             Bout[N + r] = (ph[r] - qh) * dinv[r];
         }
