@@ -177,6 +177,23 @@ PD_HD void pd_all_modes_point(const Grp& g, const PdEval& a, int b, int l, doubl
     for (int m = 0; m < a.NF; ++m) pd_mode_at<Grp, NC>(g, a, b, m, l, ts, ev, um + m * 2 * a.N);
 }
 
+// sum_m um[m * stride] cos(m dphi)  (:256-260).  cos(m dphi) by the Chebyshev recurrence
+// c_{m+1} = 2 cos(dphi) c_m - c_{m-1}: one cosine per (stream, azimuth) instead of NFourier;
+// its rounding error grows like m * eps, far below the parity tolerance for NFourier <= 64+.
+PD_HD double pd_azimuth_sum(const double* um, int stride, int NF, double dphi) {
+    const double c1 = cos(dphi), two_c1 = 2.0 * c1;
+    double cm1 = 1.0, cm = c1;
+    double s = um[0];
+    if (NF > 1) s = fma(um[stride], c1, s);
+    for (int m = 2; m < NF; ++m) {
+        const double cn = fma(two_c1, cm, -cm1);
+        s = fma(um[(long)m * stride], cn, s);
+        cm1 = cm;
+        cm = cn;
+    }
+    return s;
+}
+
 // ---------------------------------------------------------------------------
 // Nakajima-Tanaka corrections.
 // ---------------------------------------------------------------------------
@@ -194,8 +211,9 @@ PD_HD double pd_legendre_series(const double* coef, int nc, double x, const doub
     double p0 = 1.0, p1 = x;
     double s = coef[0];
     if (nc > 1) s = fma(coef[1], x, s);
-    for (int l = 1; l + 1 < nc; ++l) {
-        const double p2 = ((2 * l + 1) * x * p1 - l * p0) * rinv[l + 1];
+    double lf = 1.0;
+    for (int l = 1; l + 1 < nc; ++l, lf += 1.0) {
+        const double p2 = (fma(2.0, lf, 1.0) * x * p1 - lf * p0) * rinv[l + 1];
         s = fma(coef[l + 1], p2, s);
         p0 = p1;
         p1 = p2;
@@ -208,13 +226,23 @@ PD_HD double pd_legendre_series_raw(const double* gl, int nc, double x, const do
     double p0 = 1.0, p1 = x;
     double s = 1.0;
     if (nc > 1) s = fma(3.0 * gl[1], x, s);
-    for (int l = 1; l + 1 < nc; ++l) {
-        const double p2 = ((2 * l + 1) * x * p1 - l * p0) * rinv[l + 1];
-        s = fma((2 * l + 3) * gl[l + 1], p2, s);
+    double lf = 1.0;
+    for (int l = 1; l + 1 < nc; ++l, lf += 1.0) {
+        const double p2 = (fma(2.0, lf, 1.0) * x * p1 - lf * p0) * rinv[l + 1];
+        s = fma(fma(2.0, lf, 3.0) * gl[l + 1], p2, s);
         p0 = p1;
         p1 = p2;
     }
     return s;
+}
+
+// cosine of the scattering angle between stream i at azimuth phi and the beam (-mu0, phi0)  (subroutines.py:85-112)
+PD_HD double pd_nt_nu(const PdEval& a, int b, int i, double phi) {
+    const double* cp = a.st.colp + (long)b * PD_NCOLP;
+    const double mu0 = cp[PD_COL_MU0];
+    const double mua = a.st.mu_nodes[i < a.N ? i : i - a.N];
+    const double mus = (i < a.N) ? mua : -mua;
+    return -mu0 * mus + sqrt(1.0 - mu0 * mu0) * sqrt(1.0 - mus * mus) * cos(cp[PD_COL_PHI0] - phi);
 }
 
 // Per column pre-computation for the TMS correction, multi-layer part
@@ -297,19 +325,18 @@ PD_HD double pd_nt_value(const PdEval& a, const PdNT& nt, int b, int i, int l, d
                          const double* wall_l, const double* rinv) {
     const int n = a.N, L = a.L;
     const double* cp = a.st.colp + (long)b * PD_NCOLP;
-    const double mu0 = cp[PD_COL_MU0], I0 = cp[PD_COL_I0], phi0 = cp[PD_COL_PHI0];
+    const double mu0 = cp[PD_COL_MU0], I0 = cp[PD_COL_I0];
     const double* taus = a.st.taus + (long)b * (L + 1);
     const bool up = i < n;
     const int ii = up ? i : i - n;
     const double mua = a.st.mu_nodes[ii];
     const double mus = up ? mua : -mua;  // signed stream cosine
     const double mi = 1.0 / mua;
-    const double cphi = cos(phi0 - phi);
-    // cosine of the scattering angle between (mus, phi) and the beam (-mu0, phi0)
-    const double nu = -mu0 * mus + sqrt(1.0 - mu0 * mu0) * sqrt(1.0 - mus * mus) * cphi;
     const double fl = nt.f[(long)b * L + l];
+    const double* wtr = nt.wleg + ((long)b * L + l) * a.NLeg;
+    const double nu = pd_nt_nu(a, b, i, phi);
     const double ptrue = pd_legendre_series_raw(wall_l, a.NLeg_all, nu, rinv);
-    const double ptrun = pd_legendre_series(nt.wleg + ((long)b * L + l) * a.NLeg, a.NLeg, nu, rinv);
+    const double ptrun = pd_legendre_series(wtr, a.NLeg, nu, rinv);
     const double Bsc = nt.omega_s[(long)b * L + l] * (I0 / (4.0 * PD_PI)) * (mu0 / (mu0 + mus)) * (ptrue / (1.0 - fl) - ptrun);
     const double sc = a.st.scale_tau[(long)b * L + l];
     const double ttop = taus[l], tbot = taus[l + 1];
@@ -327,14 +354,14 @@ PD_HD double pd_nt_value(const PdEval& a, const PdNT& nt, int b, int i, int l, d
     double val = Bsc * (own + other);
     if (!up) {  // IMS, downward streams only (:613-638)
         const double mu0s = imsv[1];
-        const double nu2 = -mu0 * (-mua) + sqrt(1.0 - mu0 * mu0) * sqrt(1.0 - mua * mua) * cphi;
         const double x = mi - 1.0 / mu0s;
         double chi;
         if (a.anti)
             chi = ((mu0s - x * mu0s * (mu0s + tq)) * exp(-tq / mu0s) - mua * exp(-tq * mi)) / (mua * mu0s * x * x);
         else
             chi = ((tq - 1.0 / x) * exp(-tq / mu0s) + exp(-tq * mi) / x) / (mua * mu0s * x);
-        val += imsv[0] * pd_legendre_series(imsc, a.NLeg_all, nu2, rinv) * chi;
+        // (for a downward stream the IMS scattering angle equals nu)
+        val += imsv[0] * pd_legendre_series(imsc, a.NLeg_all, nu, rinv) * chi;
     }
     return val;
 }

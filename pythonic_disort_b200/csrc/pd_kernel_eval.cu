@@ -45,30 +45,33 @@ __global__ void k_eval_u(PdEval a, const double* __restrict__ phi_q, int nphi, i
     const double resc = cp[PD_COL_RESCALE], phi0 = cp[PD_COL_PHI0];
     for (int idx = g.lane(); idx < n2 * nphi; idx += LANES) {
         const int i = idx / nphi, p = idx - i * nphi;
-        const double dphi = phi0 - phi_q[p];
-        double s = 0.0;
-        for (int m = 0; m < a.NF; ++m) s += um[m * n2 + i] * cos((double)m * dphi);
-        u[(((long)b * n2 + i) * a.ntau + t) * nphi + p] = resc * s;
+        u[(((long)b * n2 + i) * a.ntau + t) * nphi + p] = resc * pd_azimuth_sum(um + i, n2, a.NF, phi0 - phi_q[p]);
     }
     if (ulast)
         for (int i = g.lane(); i < n2; i += LANES) ulast[((long)b * n2 + i) * a.ntau + t] = um[(a.NF - 1) * n2 + i];
 }
 
-// Nakajima-Tanaka corrections added to u in place: one CTA per column.
+// Nakajima-Tanaka corrections added to u in place: one CTA per column; warp 0 runs the TMS layer scans while
+// warp 1 prepares the IMS constants, then all threads sweep the (level, stream, azimuth) outputs.
+// (Tabulating P_l(nu) per (stream, azimuth) in shared memory and replacing the recurrences by dot products was
+// measured to be slower: two loads per FMA make it LSU bound.)
 __global__ void __launch_bounds__(256) k_nt(PdEval a, PdNT nt, const double* __restrict__ phi_q, int nphi, double* u) {
     extern __shared__ double smem[];
     const int b = blockIdx.x;
-    const int n = a.N, n2 = 2 * n, L = a.L;
+    const int n = a.N, n2 = 2 * n, L = a.L, NA = a.NLeg_all;
     double* Rpos = smem;                 // [n][L]
     double* Rneg = Rpos + n * L;         // [n][L]
     double* imsc = Rneg + n * L;         // [NLeg_all]
-    double* imsv = imsc + a.NLeg_all;    // [2]
+    double* imsv = imsc + NA;            // [2]
     double* rinv = imsv + 2;             // [NLeg_all + 1] 1/l
     if (a.st.colp[(long)b * PD_NCOLP + PD_COL_NT] == 0.0) return;  // gate of pydisort.py:375, column part
-    for (int i = threadIdx.x; i <= a.NLeg_all; i += blockDim.x) rinv[i] = (i > 0) ? 1.0 / (double)i : 0.0;
-    if (threadIdx.x < 32) {
+    for (int i = threadIdx.x; i <= NA; i += blockDim.x) rinv[i] = (i > 0) ? 1.0 / (double)i : 0.0;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) {
         SubWarp<32> g;
         if (L > 1) pd_tms_scans(g, a, b, Rpos, Rneg);
+    } else if (warp == 1) {
+        SubWarp<32> g;
         pd_ims_setup(g, a, nt, b, imsc, imsv);
     }
     __syncthreads();
@@ -82,11 +85,10 @@ __global__ void __launch_bounds__(256) k_nt(PdEval a, PdNT nt, const double* __r
         const int l = pd_locate(a.st.tau + (long)b * L, L, tq);
         const double ts = pd_scaled_tau(a, b, l, tq);
         const double v = pd_nt_value(a, nt, b, i, l, tq, ts, phi_q[p], Rpos, Rneg, imsc, imsv,
-                                     nt.leg_all + ((long)b * L + l) * a.NLeg_all, rinv);
+                                     nt.leg_all + ((long)b * L + l) * NA, rinv);
         u[(((long)b * n2 + i) * a.ntau + t) * nphi + p] += resc * v;
     }
 }
-
 
 extern "C" {
 

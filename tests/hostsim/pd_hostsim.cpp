@@ -172,10 +172,7 @@ int pd_eval_u(const pd_config* cfg, const pd_state* st, const double* tau_q, int
             pd_all_modes_point(g, a, b, l, ts, ev, um);
             for (int i = 0; i < n2; ++i) {
                 for (int q = 0; q < nphi; ++q) {
-                    const double dphi = phi0 - phi_q[q];
-                    double s = 0.0;
-                    for (int m = 0; m < a.NF; ++m) s += um[m * n2 + i] * cos((double)m * dphi);
-                    double v = resc * s;
+                    double v = resc * pd_azimuth_sum(um + i, n2, a.NF, phi0 - phi_q[q]);
                     if (ntb)
                         v += resc * pd_nt_value(a, p, b, i, l, tq, ts, phi_q[q], Rpos, Rneg, imsc, imsv,
                                                 leg_all + ((long)b * L + l) * a.NLeg_all, rinv);
