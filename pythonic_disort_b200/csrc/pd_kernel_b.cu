@@ -72,7 +72,7 @@ template <int N, int MINB, bool SH>
 __global__ void __launch_bounds__(128, MINB) k_stage_b_reg(PdStageB a, double* hist, long hist_doubles) {
     extern __shared__ double smem[];
     constexpr int LS = 4 * N;
-    constexpr int SD = (PdStageBRow<N>::SMEM_DOUBLES + 1) & ~1;
+    const int SD = (PdStageBRow<N>::smem_doubles(a.L) + 1) & ~1;
     const int gpb = blockDim.x / LS, gi = threadIdx.x / LS;
     const long slot = (long)blockIdx.x * gpb + gi;
     const long nslots = (long)gridDim.x * gpb;
@@ -95,7 +95,7 @@ template <int N, int MINB, bool SH>
 static StageBPlan plan_reg(int B, int NF, int L) {
     StageBPlan p;
     constexpr int LS = 4 * N;
-    p.sys_doubles = (PdStageBRow<N>::SMEM_DOUBLES + 1) & ~1;
+    p.sys_doubles = (PdStageBRow<N>::smem_doubles(L) + 1) & ~1;
     p.wpb = 4;
     const int gpb = p.wpb * (32 / LS);
     p.smem = (size_t)p.sys_doubles * 8 * gpb;

@@ -31,7 +31,8 @@
 template <int N>
 struct PdStageBRow {
     static constexpr int N2 = 2 * N, NR = 3 * N, RC = 4 * N, NCOL = 4 * N + 1, LDB = 4 * N + 2, HROW = 2 * N + 1;
-    static constexpr int SMEM_DOUBLES = 2 * LDB + 3 * N2 + N * N;
+    static constexpr int SMEM_FIXED = 2 * LDB + 3 * N2 + N * N;
+    PD_HD static int smem_doubles(int L) { return SMEM_FIXED + L * N + L + 1; }  // + exp(-k dtau*)[L][N], exp(-tau*/mu0)[L+1]
     static constexpr long HIST_PER_LAYER = (long)N2 * HROW;
 };
 
@@ -51,10 +52,11 @@ __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, i
     const int lane = g.lane();
     const int L = A.L;
     double* buf = sm;            // [2][LDB] published pivot row (double buffered), 16-byte aligned
-    double* E = buf + 2 * LDB;   // [2N] exp(-k dtau*) of layer l (first N) and l+1 (last N)
-    double* xs = E + N2;         // [2N]
+    double* xs = buf + 2 * LDB + N2;  // [2N]
     double* vt = xs + N2;        // [2N]
     double* R = vt + N2;         // [N][N]
+    double* Eall = R + N * N;    // [L][N]  exp(-k_l dtau*_l), all layers, computed once per system
+    double* att = Eall + (long)A.L * N;  // [L+1] exp(-tau*_l / mu0)
 
     const long sys = (long)b * A.NF + m;
     const double* taus = A.taus + (long)b * (L + 1);
@@ -83,8 +85,16 @@ __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, i
         for (int idx = lane; idx < N * N; idx += LS)
             R[idx] = ((m == 0) ? 2.0 : 1.0) * q[idx] * A.mu[idx % N] * A.w[idx % N];
     }
-    if (lane < N) E[N + lane] = exp(-Kc[lane] * (taus[1] - taus[0]));
+    // all exponentials of this system up front: independent, so their latency overlaps, and the layer loop
+    // has no transcendental on its critical path
+    for (int idx = lane; idx < L * N; idx += LS) {
+        const int ll = idx / N;
+        Eall[idx] = exp(-Kc[idx] * (taus[ll + 1] - taus[ll]));
+    }
+    if (beam)
+        for (int ll = lane; ll <= L; ll += LS) att[ll] = exp(-taus[ll] / mu0);
     g.sync();
+    const double* E = Eall;
 
     double a[NCOL];        // this lane's panel row; a[RC] is the right-hand side
     bool active = false;   // row still a pivot candidate
@@ -102,7 +112,7 @@ __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, i
 #pragma unroll
         for (int c = 0; c < N; ++c) {
             a[c] = g0[c];
-            a[N + c] = g1[c] * E[N + c];
+            a[N + c] = g1[c] * Eall[c];
         }
         double v = have_b ? bneg[lane] : 0.0;
         if (beam) v -= Bc[r];
@@ -116,14 +126,7 @@ __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, i
 
     for (int l = 0; l < L; ++l) {
         const bool last = (l == L - 1);
-        // ---- exponentials of layer l (E[0..N)) and l+1 (E[N..2N)) ----
-        double e_new = 0.0;
-        if (lane < N) e_new = E[N + lane];
-        else if (lane < N2 && !last) e_new = exp(-Kc[(l + 1) * N + (lane - N)] * (taus[l + 2] - taus[l + 1]));
-        g.sync();
-        if (lane < N2) E[lane] = e_new;
-        g.sync();
-
+        E = Eall + (long)l * N;  // E[c]: layer l, E[N + c]: layer l + 1
         // ---- pull the G block the NEXT stage will read (G_{l+2}) towards L1 while this stage computes ----
 #if defined(__CUDA_ARCH__)
         if (l + 2 < L && lane * 16 < 2 * N * N)
@@ -161,7 +164,7 @@ __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, i
                     a[3 * N + c + 1] = -w1.y * E[N + c + 1];
                 }
                 double v = 0.0;
-                if (beam) v = (Bc[(l + 1) * N2 + idx] - Bc[l * N2 + idx]) * exp(-taus[l + 1] / mu0);
+                if (beam) v = (Bc[(l + 1) * N2 + idx] - Bc[l * N2 + idx]) * att[l + 1];
                 if (dthc)
                     v += pd_thermal_at(dthc + (long)(l + 1) * A.Ns * N2, A.Ns, N2, idx, taus[l + 1]) -
                          pd_thermal_at(dthc + (long)l * A.Ns * N2, A.Ns, N2, idx, taus[l + 1]);
@@ -197,7 +200,7 @@ __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, i
                         s += (mu0 * I0 / PD_PI) * q0[idx];
                         for (int j = 0; j < N; ++j) s = fma(R[idx * N + j], Bc[l * N2 + N + j], s);
                     }
-                    v = fma(s, exp(-taus[L] / mu0), v);
+                    v = fma(s, att[L], v);
                 }
                 a[RC] = v;
                 active = hasrow = true;
