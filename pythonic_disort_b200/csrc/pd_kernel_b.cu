@@ -165,10 +165,11 @@ static bool use_r3(int N) {
     return true;
 }
 
-template <int N, bool SH>
+template <int N>
 __global__ void __launch_bounds__(64, (N == 8) ? 4 : 6) k_stage_b_r3(PdStageB a, double* hist, long hist_doubles) {
     extern __shared__ double smem[];
     const int SD = PdStageBRow3<N>::smem_doubles(a.L);
+    constexpr int GPW = 32 / N;  // systems per warp
     const int gpb = blockDim.x / N, gi = threadIdx.x / N;
     const long slot = (long)blockIdx.x * gpb + gi;
     const long nslots = (long)gridDim.x * gpb;
@@ -176,15 +177,16 @@ __global__ void __launch_bounds__(64, (N == 8) ? 4 : 6) k_stage_b_r3(PdStageB a,
     double* sm = smem + (long)gi * SD;
     double* h = hist + slot * hist_doubles;
     const long nsys = (long)a.B * a.NF;
-    for (long s = slot; s < nsys; s += nslots) pd_stage_b_row3<N, SH>(g, a, (int)(s / a.NF), (int)(s % a.NF), sm, h);
+    // warp-uniform trip count: the groups of a warp whose slot runs past the end repeat the last system, stores off
+    for (long s0 = slot - (gi % GPW); s0 < nsys; s0 += nslots) {
+        const long s = s0 + (gi % GPW);
+        const bool store = s < nsys;
+        const long se = store ? s : nsys - 1;
+        pd_stage_b_row3<N>(g, a, (int)(se / a.NF), (int)(se % a.NF), store, sm, h);
+    }
 }
 
-static bool r3_shfl() {  // pivot-row broadcast of the three-row kernel: shared memory (default) or shuffles + selects
-    const char* e = getenv("PD_STAGE_B_SHFL");
-    return e && e[0] == '1';
-}
-
-template <int N, bool SH>
+template <int N>
 static StageBPlan plan_r3(int B, int NF, int L) {
     StageBPlan p;
     p.sys_doubles = PdStageBRow3<N>::smem_doubles(L);
@@ -195,8 +197,8 @@ static StageBPlan plan_r3(int B, int NF, int L) {
     if (ctas_per_sm * p.wpb > 32) ctas_per_sm = 32 / p.wpb;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     int occ = 0;
-    if (cudaFuncSetAttribute(k_stage_b_r3<N, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stage_b_r3<N, SH>, p.wpb * 32, p.smem) == cudaSuccess && occ > 0) {
+    if (cudaFuncSetAttribute(k_stage_b_r3<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stage_b_r3<N>, p.wpb * 32, p.smem) == cudaSuccess && occ > 0) {
         if (occ < ctas_per_sm) ctas_per_sm = occ;
     } else {
         cudaGetLastError();
@@ -210,11 +212,11 @@ static StageBPlan plan_r3(int B, int NF, int L) {
     return p;
 }
 
-template <int N, bool SH>
+template <int N>
 static int launch_r3(const PdStageB& a, const StageBPlan& pb, void* workspace, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(k_stage_b_r3<N, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb.smem);
+    cudaError_t e = cudaFuncSetAttribute(k_stage_b_r3<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb.smem);
     if (e != cudaSuccess) return (int)e;
-    k_stage_b_r3<N, SH><<<pb.blocks, pb.wpb * 32, pb.smem, st>>>(a, (double*)workspace, pb.hist_doubles);
+    k_stage_b_r3<N><<<pb.blocks, pb.wpb * 32, pb.smem, st>>>(a, (double*)workspace, pb.hist_doubles);
     return (int)cudaGetLastError();
 }
 
@@ -247,10 +249,7 @@ static StageBPlan plan_fast(int B, int NF, int L, int ls) {
 }
 
 StageBPlan pd_plan_stage_b(int B, int NF, int N, int L) {
-    if (use_r3(N)) {
-        if (r3_shfl()) return (N == 4) ? plan_r3<4, true>(B, NF, L) : plan_r3<8, true>(B, NF, L);
-        return (N == 4) ? plan_r3<4, false>(B, NF, L) : plan_r3<8, false>(B, NF, L);
-    }
+    if (use_r3(N)) return (N == 4) ? plan_r3<4>(B, NF, L) : plan_r3<8>(B, NF, L);
     if (use_reg(N)) return plan_reg_any(B, NF, N, L);
     if (const int ls = fast_lanes(N)) {
         if (N == 4) return plan_fast<4>(B, NF, L, ls);
@@ -296,10 +295,7 @@ int pd_launch_stage_b(const PdStageB& a, void* workspace, size_t workspace_bytes
     const StageBPlan pb = pd_plan_stage_b(a.B, a.NF, a.N, a.L);
     if (workspace_bytes < (size_t)pb.slots * pb.hist_doubles * 8 || !workspace) return -20;
     if (pb.smem > PD_SMEM_MAX_CTA) return -21;
-    if (use_r3(a.N)) {
-        if (r3_shfl()) return (a.N == 4) ? launch_r3<4, true>(a, pb, workspace, st) : launch_r3<8, true>(a, pb, workspace, st);
-        return (a.N == 4) ? launch_r3<4, false>(a, pb, workspace, st) : launch_r3<8, false>(a, pb, workspace, st);
-    }
+    if (use_r3(a.N)) return (a.N == 4) ? launch_r3<4>(a, pb, workspace, st) : launch_r3<8>(a, pb, workspace, st);
     if (use_reg(a.N)) return launch_reg_any(a, pb, workspace, st);
     if (const int ls = fast_lanes(a.N)) {
         const int key = a.N * 100 + ls;

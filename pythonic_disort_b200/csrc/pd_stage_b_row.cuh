@@ -48,7 +48,7 @@ template <int N, int LS, bool SHFL_BCAST>
 __device__ void pd_stage_b_row(const SubWarp<LS>& g, const PdStageB& A, int b, int m, double* sm, double* hist) {
     using F = PdStageBRow<N>;
     static_assert(LS >= 3 * N, "one lane per panel row");
-    constexpr int N2 = F::N2, NR = F::NR, RC = F::RC, NCOL = F::NCOL, LDB = F::LDB, HROW = F::HROW;
+    constexpr int N2 = F::N2, NR = F::NR, RC = F::RC, NCOL = F::NCOL, LDB = F::LDB;
     const int lane = g.lane();
     const int L = A.L;
     double* buf = sm;            // [2][LDB] published pivot row (double buffered), 16-byte aligned

@@ -5,13 +5,18 @@
 // costs two SHFL (64 bit) and feeds a single DFMA per lane, and SHFL issues at half the DFMA
 // rate (profiles/r1_summary_final.md).  Here a system is owned by N lanes and every lane keeps
 // three of the 3N panel rows in registers, so that
-//   * one broadcast entry feeds three DFMAs per lane, and one SHFL serves 32/N systems at once
-//     (shuffle instructions per system drop by 32/N; lanes are 100 % occupied, 3N rows on N lanes);
-//   * the pivot row lives in register row `pr` of lane `pl`; every lane selects its own row `pr`
-//     (two SEL per 32-bit half) and the shuffle picks lane pl's copy;
+//   * lanes are 100 % occupied (3N rows on N lanes) and a warp works on 32/N systems at once;
+//   * one broadcast pivot-row entry feeds three DFMAs per lane: the lane that owns the pivot row
+//     publishes it to shared memory with 128-bit stores (three predicated copies of the store loop,
+//     one per register row, so no register-row selects), the other lanes read it back with
+//     128-bit broadcast loads -- about 0.5 load-store instructions per DFMA instead of 2 shuffles;
 //   * pivot search: per-lane maximum of a 32-bit key (upper word of |a|, low 5 bits = 31 - slot)
 //     then a log2(N)-step butterfly -- partial pivoting up to a relative 2^-15 in the magnitude
-//     comparison, which is all the stability argument needs;
+//     comparison, which is all the stability argument needs; every lane also prepares 1/candidate
+//     so that the reciprocal of the pivot is published with the row;
+//   * all warp-level primitives use the full mask: the systems of a warp run in lock step (same L,
+//     same N; the kernel loop is warp-uniform and pads the last warp with a repeated system whose
+//     stores are suppressed), which avoids the MATCH-based sub-mask barrier;
 //   * as before rows never move: a pivot row leaves the game, Gauss-Jordan keeps updating it, and at
 //     the end of the stage it holds its row of U11^-1 [U12 | y] up to 1/pivot; the N rows that were
 //     never pivots are the carry of the next stage, the 2N freed slots load the next interface.
@@ -27,8 +32,8 @@ struct PdStageBRow3 {
     static constexpr int LPS = N, RPL = 3;  // lanes per system, rows per lane
     static constexpr int N2 = 2 * N, RC = 4 * N, NCOL = 4 * N + 1, HROW = 2 * N + 1;
     static constexpr int LDB = 4 * N + 2;   // published pivot row (even length: 128-bit accesses)
-    static constexpr int SMEM_FIXED = 2 * LDB + N2 + N * N;
-    // buf[2][LDB], xs, R, exp(-k dtau*)[L][N], exp(-tau*/mu0)[L+1]; the per-system stride is 2 (mod 16) doubles so that
+    static constexpr int SMEM_FIXED = 2 * LDB + 2 * N2 + N * N;
+    // buf[2][LDB], xs, 1/pivot of the stage, R, exp(-k dtau*)[L][N], exp(-tau*/mu0)[L+1]; the per-system stride is 2 (mod 16) doubles so that
     // the 32/N systems of a warp read their pivot rows from disjoint 16-byte bank groups
     PD_HD static int smem_doubles(int L) { return ((SMEM_FIXED + L * N + L + 1 + 13) / 16) * 16 + 2; }
     static constexpr long HIST_PER_LAYER = (long)N2 * HROW;
@@ -40,17 +45,17 @@ __device__ __forceinline__ unsigned pd_pivot_key(double v, bool act, int slot) {
     return act ? ((hi & ~31u) | (unsigned)(31 - slot)) : 0u;
 }
 
-template <int N, bool SHFL_BCAST>
-__device__ void pd_stage_b_row3(const SubWarp<N>& g, const PdStageB& A, int b, int m, double* sm, double* hist) {
+template <int N>
+__device__ void pd_stage_b_row3(const SubWarp<N>& g, const PdStageB& A, int b, int m, bool store, double* sm, double* hist) {
     using F = PdStageBRow3<N>;
     constexpr int LPS = F::LPS, N2 = F::N2, RC = F::RC, NCOL = F::NCOL;
-    constexpr int LOGL = (LPS == 8) ? 3 : 2;
     static_assert(N == 4 || N == 8, "three rows per lane: N = 4 or 8");
     const int lane = g.lane();
     const int L = A.L;
     double* buf = sm;                    // [2][LDB] published pivot row, double buffered (shared-memory broadcast variant)
     double* xs = buf + 2 * F::LDB;       // [2N]
-    double* R = xs + N2;                 // [N][N]
+    double* pinvs = xs + N2;             // [2N] 1/pivot of every step of the current stage
+    double* R = pinvs + N2;              // [N][N]
     double* Eall = R + N * N;            // [L][N]  exp(-k_l dtau*_l)
     double* att = Eall + (long)L * N;    // [L+1]   exp(-tau*_l / mu0)
 
@@ -87,19 +92,17 @@ __device__ void pd_stage_b_row3(const SubWarp<N>& g, const PdStageB& A, int b, i
     }
     if (beam)
         for (int ll = lane; ll <= L; ll += LPS) att[ll] = exp(-taus[ll] / mu0);
-    g.sync();
+    __syncwarp();
 
     double a[3][NCOL];   // slot (lane, r) = panel row r * LPS + lane; a[r][RC] is the right-hand side
     bool active[3];      // row still a pivot candidate
     int myj[3];          // pivot step at which the row was used in this stage (-1: not a pivot row)
-    double mypinv[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
 #pragma unroll
         for (int c = 0; c < NCOL; ++c) a[r][c] = 0.0;
         active[r] = false;
         myj[r] = (r == 0) ? -1 : 0;  // register rows 1 and 2 are free at stage 0
-        mypinv[r] = 0.0;
     }
 
     // ---- top boundary rows: register row 0 of every lane (the carry of stage 0) ----
@@ -128,7 +131,7 @@ __device__ void pd_stage_b_row3(const SubWarp<N>& g, const PdStageB& A, int b, i
         // ---- carry rows shift by 2N columns; freed slots take the new rows ----
         unsigned fr[3];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) fr[r] = (__ballot_sync(g.mask, myj[r] >= 0) >> gbase) & ((1u << LPS) - 1u);
+        for (int r = 0; r < 3; ++r) fr[r] = (__ballot_sync(0xffffffffu, myj[r] >= 0) >> gbase) & ((1u << LPS) - 1u);
         pd_static_for<0, 3>([&](auto RI) {
             constexpr int r = decltype(RI)::value;
             if (l > 0 && active[r]) {
@@ -211,125 +214,128 @@ __device__ void pd_stage_b_row3(const SubWarp<N>& g, const PdStageB& A, int b, i
         });
 
         // ---- Gauss-Jordan elimination of the 2N columns of C_l, partial pivoting over the rows in play ----
-        auto find = [&](auto JI) -> int {
+        // Per step: the pivot lane publishes its pivot row and the reciprocal of the pivot (128-bit stores, double
+        // buffered), one warp barrier, every lane reads the row back with broadcast loads and updates its three rows.
+        // The search for the NEXT pivot (key per row, per-lane maximum, log2(N) butterfly steps) and the reciprocal of
+        // each lane's own candidate are started as soon as column j+1 has been updated and are interleaved with
+        // the remaining columns, so that neither the shuffle nor the MUFU/Newton latency sits on the critical path.
+        unsigned kbest;   // this lane's best key for the coming step
+        double rcand;     // 1 / (this lane's candidate pivot)
+        int rbest;        // register row of this lane's candidate
+        auto local_best = [&](auto JI) {
             constexpr int j = decltype(JI)::value;
-            unsigned k = pd_pivot_key<LPS>(a[0][j], active[0], lane);
-            k = max(k, pd_pivot_key<LPS>(a[1][j], active[1], LPS + lane));
-            k = max(k, pd_pivot_key<LPS>(a[2][j], active[2], 2 * LPS + lane));
-#pragma unroll
-            for (int o = LPS / 2; o > 0; o >>= 1) k = max(k, __shfl_xor_sync(g.mask, k, o, LPS));
-            if ((k & ~31u) == 0u) status |= PD_ST_ZERO_PIVOT;
-            return 31 - (int)(k & 31u);
+            const unsigned k0 = pd_pivot_key<LPS>(a[0][j], active[0], lane);
+            const unsigned k1 = pd_pivot_key<LPS>(a[1][j], active[1], LPS + lane);
+            const unsigned k2 = pd_pivot_key<LPS>(a[2][j], active[2], 2 * LPS + lane);
+            kbest = max(k0, max(k1, k2));
+            rbest = (k0 == kbest) ? 0 : ((k1 == kbest) ? 1 : 2);
+            rcand = pd_rcp((rbest == 0) ? a[0][j] : ((rbest == 1) ? a[1][j] : a[2][j]));
         };
-        int p = find(std::integral_constant<int, 0>{});
+        local_best(std::integral_constant<int, 0>{});
+        unsigned kall = kbest;
+#pragma unroll
+        for (int o = LPS / 2; o > 0; o >>= 1) kall = max(kall, __shfl_xor_sync(0xffffffffu, kall, o, LPS));
         pd_static_for<0, N2>([&](auto JI) {
             constexpr int j = decltype(JI)::value;
-            const int pl = p & (LPS - 1), pr = p >> LOGL;
-            const bool s0 = pr == 0, s1 = pr == 1;
-            auto sel = [&](int c) -> double { return s0 ? a[0][c] : (s1 ? a[1][c] : a[2][c]); };
-            if constexpr (SHFL_BCAST) {
-            const double piv = __shfl_sync(g.mask, sel(j), pl, LPS);
-            const double pinv = pd_rcp(piv);
-            double mneg[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                mneg[r] = -a[r][j] * pinv;
-                if (lane == pl && pr == r) {
-                    active[r] = false;
-                    myj[r] = j;
-                    mypinv[r] = pinv;
-                    mneg[r] = 0.0;
-                }
-            }
-            if constexpr (j + 1 < N2) {  // column j+1 first, then start looking for the next pivot
-                const double u = __shfl_sync(g.mask, sel(j + 1), pl, LPS);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) a[r][j + 1] = fma(mneg[r], u, a[r][j + 1]);
-                p = find(std::integral_constant<int, (j + 1 < N2) ? j + 1 : j>{});
-            }
-            constexpr int cs = (j + 1 < N2) ? j + 2 : j + 1;
-#pragma unroll
-            for (int c = cs; c < NCOL; ++c) {
-                const double u = __shfl_sync(g.mask, sel(c), pl, LPS);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) a[r][c] = fma(mneg[r], u, a[r][c]);
-            }
-            } else {
-            // the pivot lane publishes its pivot row (columns j..4N) to shared memory, 128 bits at a time;
-            // every lane of the system reads it back with broadcast loads: no selects, no shuffles
+            if ((kall & ~31u) == 0u) status |= PD_ST_ZERO_PIVOT;
+            const bool mine = (kall == kbest);  // keys are unique (slot bits): exactly one lane of the system owns the pivot
             double* pb = buf + (j & 1) * F::LDB;
             constexpr int c0 = j & ~1;
-            if (lane == pl) {
+            if (mine) {
                 pd_static_for<0, 3>([&](auto RI) {
                     constexpr int r = decltype(RI)::value;
-                    if (pr == r) {
+                    if (rbest == r) {
 #pragma unroll
                         for (int c = c0; c < NCOL; c += 2) {
                             pd_d2 v2;
                             v2.x = a[r][c];
-                            v2.y = (c + 1 < NCOL) ? a[r][c + 1] : 0.0;
+                            v2.y = (c + 1 < NCOL) ? a[r][c + 1] : rcand;
                             *reinterpret_cast<pd_d2*>(pb + c) = v2;
                         }
                     }
                 });
             }
-            g.sync();
-            const double pinv = pd_rcp(pb[j]);
+            __syncwarp();
+            const pd_d2 tail = *reinterpret_cast<const pd_d2*>(pb + RC);  // (right-hand side, 1/pivot)
+            const double pinv = tail.y;
             double mneg[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 mneg[r] = -a[r][j] * pinv;
-                if (lane == pl && pr == r) {
+                if (mine && rbest == r) {
                     active[r] = false;
                     myj[r] = j;
-                    mypinv[r] = pinv;
                     mneg[r] = 0.0;
                 }
             }
+            if (lane == 0) pinvs[j] = pinv;
+            constexpr int cs = (j + 1 < N2) ? j + 2 : j + 1;  // first column still to update after column j+1
+            constexpr int c1 = cs & ~1;
+            constexpr int NPAIR = (RC - c1) / 2;             // full pairs below the (rhs, 1/pivot) pair
+            constexpr int NST = (LPS == 8) ? 3 : 2;          // butterfly steps
+            constexpr int CH = (NPAIR + NST) / (NST + 1);    // pairs per chunk
+            unsigned knew = 0u, kt = 0u;
             if constexpr (j + 1 < N2) {
                 const double u = pb[j + 1];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) a[r][j + 1] = fma(mneg[r], u, a[r][j + 1]);
-                p = find(std::integral_constant<int, (j + 1 < N2) ? j + 1 : j>{});
+                local_best(std::integral_constant<int, (j + 1 < N2) ? j + 1 : j>{});
+                knew = kbest;
+                kt = __shfl_xor_sync(0xffffffffu, knew, LPS / 2, LPS);
             }
-            constexpr int cs = (j + 1 < N2) ? j + 2 : j + 1;
-            constexpr int c1 = cs & ~1;
+            pd_static_for<0, NST + 1>([&](auto QI) {
+                constexpr int q = decltype(QI)::value;
+                constexpr int lo = q * CH, hi = (q + 1) * CH < NPAIR ? (q + 1) * CH : NPAIR;
+                if constexpr (hi > lo) {
+                    pd_d2 ur[hi - lo];
 #pragma unroll
-            for (int c = c1; c < NCOL; c += 2) {
-                const pd_d2 u = *reinterpret_cast<const pd_d2*>(pb + c);
-                if (c >= cs) {
+                    for (int i = lo; i < hi; ++i) ur[i - lo] = *reinterpret_cast<const pd_d2*>(pb + c1 + 2 * i);
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) a[r][c] = fma(mneg[r], u.x, a[r][c]);
+                    for (int i = lo; i < hi; ++i) {
+                        const int c = c1 + 2 * i;
+                        if (c >= cs) {
+#pragma unroll
+                            for (int r = 0; r < 3; ++r) a[r][c] = fma(mneg[r], ur[i - lo].x, a[r][c]);
+                        }
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) a[r][c + 1] = fma(mneg[r], ur[i - lo].y, a[r][c + 1]);
+                    }
                 }
-                if (c + 1 < NCOL) {
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) a[r][c + 1] = fma(mneg[r], u.y, a[r][c + 1]);
+                if constexpr (j + 1 < N2 && q < NST) {
+                    knew = max(knew, kt);
+                    if constexpr (q + 1 < NST) kt = __shfl_xor_sync(0xffffffffu, knew, LPS >> (q + 2), LPS);
                 }
-            }
-            }
+            });
+#pragma unroll
+            for (int r = 0; r < 3; ++r) a[r][RC] = fma(mneg[r], tail.x, a[r][RC]);
+            kall = knew;
         });
 
         // ---- pivot row of step j holds row j of U11^-1 [U12 | y] up to 1/pivot: history [column][row] ----
+        __syncwarp();  // pinvs of the last step
         pd_static_for<0, 3>([&](auto RI) {
             constexpr int r = decltype(RI)::value;
             if (myj[r] >= 0) {
+                const double mypinv = pinvs[myj[r]];
                 if (!last) {
                     double* h = hist + (long)l * F::HIST_PER_LAYER + myj[r];
 #pragma unroll
-                    for (int c = 0; c < N2; ++c) h[c * N2] = -a[r][N2 + c] * mypinv[r];
-                    h[N2 * N2] = a[r][RC] * mypinv[r];
+                    for (int c = 0; c < N2; ++c) h[c * N2] = -a[r][N2 + c] * mypinv;
+                    h[N2 * N2] = a[r][RC] * mypinv;
                 } else {
-                    xs[myj[r]] = a[r][RC] * mypinv[r];
+                    xs[myj[r]] = a[r][RC] * mypinv;
                 }
             }
         });
     }
-    g.sync();
+    __syncwarp();
 
     // ---- back sweep: x_l = z_l + M_l x_{l+1}; every lane owns entries lane and lane + N ----
     double* Cout = A.C + sys * L * N2;
-    Cout[(long)(L - 1) * N2 + lane] = xs[lane];
-    Cout[(long)(L - 1) * N2 + LPS + lane] = xs[LPS + lane];
+    if (store) {
+        Cout[(long)(L - 1) * N2 + lane] = xs[lane];
+        Cout[(long)(L - 1) * N2 + LPS + lane] = xs[LPS + lane];
+    }
     double h0[N2 + 1], h1[N2 + 1];
     if (L >= 2) {
         const double* h = hist + (long)(L - 2) * F::HIST_PER_LAYER;
@@ -355,14 +361,16 @@ __device__ void pd_stage_b_row3(const SubWarp<N>& g, const PdStageB& A, int b, i
                 h1[c] = h[c * N2 + LPS + lane];
             }
         }
-        g.sync();
+        __syncwarp();
         xs[lane] = s0;
         xs[LPS + lane] = s1;
-        Cout[(long)l * N2 + lane] = s0;
-        Cout[(long)l * N2 + LPS + lane] = s1;
-        g.sync();
+        if (store) {
+            Cout[(long)l * N2 + lane] = s0;
+            Cout[(long)l * N2 + LPS + lane] = s1;
+        }
+        __syncwarp();
     }
-    if (status && lane == 0) atomicOr(A.status + b, status);
+    if (status && lane == 0 && store) atomicOr(A.status + b, status);
 }
 
 #endif  // __CUDACC__

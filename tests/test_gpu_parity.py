@@ -83,7 +83,6 @@ def test_cuda_tensor_inputs_give_cuda_outputs():
 
 @pytest.mark.parametrize("env", [
     {"PD_STAGE_A_GENERAL": "1"},                              # Hessenberg-QR eigen kernel instead of Cholesky+Jacobi
-    {"PD_STAGE_B_SHFL": "1"},                                 # three-row register kernel, shuffle broadcast
     {"PD_STAGE_B_ROW1": "1"},                                 # one-row-per-lane register kernel (shuffle broadcast)
     {"PD_STAGE_B_ROW1": "1", "PD_STAGE_B_SHFL": "0"},         # ... shared-memory broadcast
     {"PD_STAGE_B_SMEM": "1"},                                 # shared-memory panel kernel instead of register rows
