@@ -5,6 +5,7 @@
 #include "pd_stage_b_fast.cuh"
 #include "pd_stage_b_row.cuh"
 #include "pd_stage_b_row3.cuh"
+#include "pd_stage_b_mma.cuh"
 
 template <int NC>
 __global__ void k_stage_b(PdStageB a, double* hist, long hist_doubles, int sys_doubles) {
@@ -220,6 +221,67 @@ static int launch_r3(const PdStageB& a, const StageBPlan& pb, void* workspace, c
     return (int)cudaGetLastError();
 }
 
+// tensor-core kernel (N = 8, 16; default): one warp per system, panel in DMMA accumulator tiles
+static bool use_mma(int N) {
+    if (N != 8 && N != 16) return false;
+    if (const char* e = getenv("PD_STAGE_B_MMA"))
+        if (e[0] == '0') return false;
+    if (const char* e = getenv("PD_STAGE_B_SMEM"))
+        if (e[0] == '1') return false;
+    if (const char* e = getenv("PD_STAGE_B_GENERIC"))
+        if (e[0] == '1') return false;
+    return true;
+}
+
+template <int N>
+__global__ void __launch_bounds__(128, (N == 8) ? 4 : 2) k_stage_b_mma(PdStageB a, double* hist, long hist_doubles) {
+    extern __shared__ double smem[];
+    const int SD = PdStageBMma<N>::smem_doubles(a.L);
+    const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5;
+    const long slot = (long)blockIdx.x * wpb + w;
+    const long nslots = (long)gridDim.x * wpb;
+    const long nsys = (long)a.B * a.NF;
+    for (long s = slot; s < nsys; s += nslots)
+        pd_stage_b_mma<N>(a, (int)(s / a.NF), (int)(s % a.NF), smem + (long)w * SD, hist + slot * hist_doubles);
+}
+
+template <int N>
+static StageBPlan plan_mma(int B, int NF, int L) {
+    StageBPlan p;
+    p.sys_doubles = PdStageBMma<N>::smem_doubles(L);
+    p.wpb = 4;
+    p.smem = (size_t)p.sys_doubles * 8 * p.wpb;
+    int ctas_per_sm = (int)(PD_SMEM_BUDGET / p.smem);
+    if (ctas_per_sm * p.wpb > 32) ctas_per_sm = 32 / p.wpb;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    int occ = 0;
+    if (cudaFuncSetAttribute(k_stage_b_mma<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stage_b_mma<N>, p.wpb * 32, p.smem) == cudaSuccess && occ > 0) {
+        if (occ < ctas_per_sm) ctas_per_sm = occ;
+    } else {
+        cudaGetLastError();
+    }
+    if (const char* e = getenv("PD_STAGE_B_CTAS")) {
+        const int v = atoi(e);
+        if (v >= 1 && v < ctas_per_sm) ctas_per_sm = v;
+    }
+    const long nsys = (long)B * NF;
+    long blocks = (nsys + p.wpb - 1) / p.wpb;
+    if (blocks > (long)PD_NUM_SMS * ctas_per_sm) blocks = (long)PD_NUM_SMS * ctas_per_sm;
+    p.blocks = (int)blocks;
+    p.slots = blocks * p.wpb;
+    p.hist_doubles = (long)L * PdStageBMma<N>::HIST_PER_LAYER;
+    return p;
+}
+
+template <int N>
+static int launch_mma(const PdStageB& a, const StageBPlan& pb, void* workspace, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(k_stage_b_mma<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb.smem);
+    if (e != cudaSuccess) return (int)e;
+    k_stage_b_mma<N><<<pb.blocks, pb.wpb * 32, pb.smem, st>>>(a, (double*)workspace, pb.hist_doubles);
+    return (int)cudaGetLastError();
+}
+
 template <int N>
 static StageBPlan plan_fast(int B, int NF, int L, int ls) {
     StageBPlan p;
@@ -249,6 +311,7 @@ static StageBPlan plan_fast(int B, int NF, int L, int ls) {
 }
 
 StageBPlan pd_plan_stage_b(int B, int NF, int N, int L) {
+    if (use_mma(N)) return (N == 8) ? plan_mma<8>(B, NF, L) : plan_mma<16>(B, NF, L);
     if (use_r3(N)) return (N == 4) ? plan_r3<4>(B, NF, L) : plan_r3<8>(B, NF, L);
     if (use_reg(N)) return plan_reg_any(B, NF, N, L);
     if (const int ls = fast_lanes(N)) {
@@ -295,6 +358,7 @@ int pd_launch_stage_b(const PdStageB& a, void* workspace, size_t workspace_bytes
     const StageBPlan pb = pd_plan_stage_b(a.B, a.NF, a.N, a.L);
     if (workspace_bytes < (size_t)pb.slots * pb.hist_doubles * 8 || !workspace) return -20;
     if (pb.smem > PD_SMEM_MAX_CTA) return -21;
+    if (use_mma(a.N)) return (a.N == 8) ? launch_mma<8>(a, pb, workspace, st) : launch_mma<16>(a, pb, workspace, st);
     if (use_r3(a.N)) return (a.N == 4) ? launch_r3<4>(a, pb, workspace, st) : launch_r3<8>(a, pb, workspace, st);
     if (use_reg(a.N)) return launch_reg_any(a, pb, workspace, st);
     if (const int ls = fast_lanes(a.N)) {

@@ -1,0 +1,480 @@
+// pd_stage_b_mma.cuh -- boundary-condition solve on the FP64 tensor cores (production path for N = 8, 16).
+//
+// Measured on B200 (tools/ubench/dmma_rate.cu, profiles/r1_dmma_ubench.txt): mma.sync.m8n8k4.f64 reaches
+// 37.1 TFLOP/s with ONE warp per scheduler and a single dependent chain, i.e. the vector-DFMA peak (34.1) at an
+// eighth of the issue slots and with no operand broadcasts.  The register kernels (pd_stage_b_row*.cuh) are bound by
+// exactly those: issue slots and the shuffle / shared-memory broadcasts of the pivot row.  So here the elimination
+// of a stage is done in blocks of four pivot columns and every block's update of the rest of the panel is one
+// rank-4 product on the tensor cores.
+//
+// One warp owns one (column, mode) system.  The 3N x 4N panel of stage l (N carried rows + 2N rows of interface l;
+// _solve_for_coeffs.py:139-323 as in pd_stage_b.cuh) lives in registers as RT x CT accumulator tiles of
+// mma.m8n8k4 (tile row = lane / 4, tile columns = 2 (lane % 4) + {0, 1}) and is mirrored in shared memory, from
+// where the other layouts are picked up.  Per block of four columns J = j0 .. j0 + 3:
+//   1. the live tiles are stored to the mirror; every lane picks up the four J-values of "its" row (one lane per
+//      row; the right-hand side lives in this layout and is eliminated like a fifth column);
+//   2. the four pivots are found one after the other with partial pivoting over the rows still in play (32-bit
+//      magnitude key + REDUX.MAX; the pivot lane publishes its four values, its multipliers, its right-hand side
+//      and -1/pivot in one small packet).  The elimination is Gauss-Jordan without normalisation (earlier pivot
+//      rows keep being reduced) and is applied to the four block columns only; every row accumulates its multipliers
+//      g with respect to the ORIGINAL four pivot rows:   new_row_i = row_i + sum_k g[i][k] * row_{p_k};
+//   3. A = g (3N x 4, through shared memory) and B = the four pivot rows (4 x 4N, from the mirror) are loaded in
+//      operand layout and every live tile gets one DMMA:  C = A B + C.
+// After the 2N/4 blocks the pivot row of column j holds pivot_j times row j of U11^-1 [U12 | y]; M_l = -U12 and z_l
+// go to the history buffer, the N rows that were never pivots are the next stage's carry (their columns shift by
+// 2N: a move of whole tiles), and the freed rows load interface l + 1.  Back substitution x_l = z_l + M_l x_{l+1}.
+// Rows never move; pivot choice equals dgbsv's up to ties and a relative 2^-14 in the magnitude comparison.
+#pragma once
+#include <type_traits>
+
+#include "pd_stage_b_row.cuh"
+
+#if defined(__CUDACC__)
+
+template <int N>
+struct PdStageBMma {
+    static_assert(N % 8 == 0 && N <= 16, "tensor-core stage B: N = 8 or 16");
+    static constexpr int N2 = 2 * N, NR = 3 * N, RC = 4 * N, RT = NR / 8, CT = RC / 8, HT = CT / 2, NB = N2 / 4;
+    static constexpr int RPL = (NR + 31) / 32;  // rows per lane in the one-lane-per-row layout
+    static constexpr int NT8 = N / 8;           // tiles per N columns
+    static constexpr int BLK = NR * 4;          // block columns / multipliers: [NR][4]
+    static constexpr int PS = RC + 4;           // stride of a published pivot row: 4 (mod 16) doubles, so that the
+                                                // operand loads of a half warp touch 16 distinct bank pairs
+    static constexpr int SMEM_FIXED = 2 * BLK + 4 * PS + N * N + N2 + NR / 2;
+    PD_HD static int smem_doubles(int L) { return (SMEM_FIXED + L * N + L + 1 + 1) & ~1; }
+    static constexpr long HIST_PER_LAYER = (long)N2 * N2 + N2;  // M_l [2N][2N] row-major, z_l [2N]
+    using mask_t = typename std::conditional<(NR > 32), unsigned long long, unsigned>::type;
+};
+
+__device__ __forceinline__ int pd_popc(unsigned v) { return __popc(v); }
+__device__ __forceinline__ int pd_popc(unsigned long long v) { return __popcll(v); }
+
+// D = A (8x4, row) * B (4x8, col) + D on the FP64 tensor cores
+__device__ __forceinline__ void pd_dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int N>
+__device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, double* hist) {
+    using F = PdStageBMma<N>;
+    using mask_t = typename F::mask_t;
+    constexpr int N2 = F::N2, NR = F::NR, RC = F::RC, RT = F::RT, CT = F::CT, HT = F::HT, NB = F::NB, RPL = F::RPL;
+    constexpr int NT8 = F::NT8, PS = F::PS;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, q = lane >> 2, t = lane & 3;
+    const int L = A.L;
+    double* blkV = sm;                   // [NR][4] the block's four columns, one row per slot
+    double* blkA = blkV + F::BLK;        // [NR][4] A operand: -g
+    double* prow = blkA + F::BLK;        // [4][PS] the block's four pivot rows (B operand)
+    double* R = prow + 4 * PS;           // [N][N]
+    double* xs = R + N * N;              // [2N]
+    int* colOf = reinterpret_cast<int*>(xs + N2);  // [NR] pivot column of a row slot in this stage, -1: none
+    double* Eall = xs + N2 + NR / 2;     // [L][N]  exp(-k_l dtau*_l)
+    double* att = Eall + (long)L * N;    // [L+1]   exp(-tau*_l / mu0)
+
+    const long sys = (long)b * A.NF + m;
+    const double* taus = A.taus + (long)b * (L + 1);
+    const double* Kc = A.K + sys * L * N;
+    const double* Gc = A.G + sys * L * 2 * N * N;
+    const double* Bc = A.beam ? A.Bv + sys * L * N2 : nullptr;
+    const double* dthc = (A.iso && m == 0) ? A.dth + (long)b * L * A.Ns * N2 : nullptr;
+    const double mu0 = A.colp[(long)b * PD_NCOLP + PD_COL_MU0];
+    const double I0 = A.colp[(long)b * PD_NCOLP + PD_COL_I0];
+    const bool beam = A.beam && I0 > 0.0;
+    const bool has_bdrf = A.NBDRF > m;
+    const bool have_b = (m == 0) || (A.NFb > 1);
+    const double* bpos = A.bpos + ((long)b * A.NFb + (A.NFb > 1 ? m : 0)) * N;
+    const double* bneg = A.bneg + ((long)b * A.NFb + (A.NFb > 1 ? m : 0)) * N;
+    int status = 0;
+
+    auto Grow = [&](int l, int r, int half) -> const double* {  // the N entries G_l[r][half*N .. half*N+N)
+        const int rb = r >= N;
+        return Gc + ((long)l * 2 + (rb ^ half)) * N * N + (r - rb * N) * N;
+    };
+    auto bit = [](mask_t mk, int s) -> bool { return (mk >> s) & (mask_t)1; };
+    auto below = [](int s) -> mask_t { return ((mask_t)1 << s) - (mask_t)1; };
+    constexpr mask_t ALL = (NR == 8 * (int)sizeof(mask_t)) ? ~(mask_t)0 : (((mask_t)1 << NR) - (mask_t)1);
+
+    if (has_bdrf) {
+        const double* qm = A.bdrf_q + ((A.bdrf_percol ? (long)b * A.NBDRF : 0) + m) * N * N;
+        for (int idx = lane; idx < N * N; idx += 32) R[idx] = ((m == 0) ? 2.0 : 1.0) * qm[idx] * A.mu[idx % N] * A.w[idx % N];
+    }
+    for (int idx = lane; idx < L * N; idx += 32) {
+        const int ll = idx / N;
+        Eall[idx] = exp(-Kc[idx] * (taus[ll + 1] - taus[ll]));
+    }
+    if (beam)
+        for (int ll = lane; ll <= L; ll += 32) att[ll] = exp(-taus[ll] / mu0);
+    __syncwarp();
+
+    double c[RT][CT][2];  // accumulator tiles: row slot rt*8 + q, columns ct*8 + 2t + {0, 1}
+    double rhs[RPL];      // right-hand side of row slot lane + 32 r
+    int pj[RPL];          // pivot column of that slot in the current stage (-1: none)
+#pragma unroll
+    for (int rt = 0; rt < RT; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < CT; ++ct) c[rt][ct][0] = c[rt][ct][1] = 0.0;
+
+    // ---- top boundary rows: slots 0 .. N-1 (the carry of stage 0) ----
+#pragma unroll
+    for (int rt = 0; rt < NT8; ++rt) {
+        const int r = N + rt * 8 + q;  // downward streams
+#pragma unroll
+        for (int ct = 0; ct < HT; ++ct) {
+            const int nb = ct / NT8, cc0 = (ct % NT8) * 8 + 2 * t;
+            pd_d2 v = *reinterpret_cast<const pd_d2*>(Grow(0, r, nb) + cc0);
+            if (nb == 1) {
+                v.x *= Eall[cc0];
+                v.y *= Eall[cc0 + 1];
+            }
+            c[rt][ct][0] = v.x;
+            c[rt][ct][1] = v.y;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const int slot = lane + 32 * r;
+        double v = 0.0;
+        if (slot < N) {
+            v = have_b ? bneg[slot] : 0.0;
+            if (beam) v -= Bc[N + slot];
+            if (dthc) v -= pd_thermal_at(dthc, A.Ns, N2, N + slot, taus[0]);
+        }
+        rhs[r] = v;
+        pj[r] = -1;
+    }
+    mask_t freem = ALL & ~below(N);  // slots that take new rows at the start of the coming stage
+
+    for (int l = 0; l < L; ++l) {
+        const bool last = (l == L - 1);
+        const double* E = Eall + (long)l * N;  // E[c]: layer l, E[N + c]: layer l + 1
+        if (l + 2 < L && lane * 16 < 2 * N * N)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(Gc + ((long)(l + 2) * 2) * N * N + lane * 16));
+
+        // ---- rows in play: the carry (never a pivot) plus the new rows ----
+        mask_t active;
+        if (!last) {
+            active = ALL;
+        } else {  // only N new rows: the first N free slots
+            mask_t fm = freem, firstN = 0;
+            for (int i = 0; i < N; ++i) {
+                const mask_t low = fm & (~fm + 1);
+                firstN |= low;
+                fm ^= low;
+            }
+            active = (ALL & ~freem) | firstN;
+        }
+
+        // ---- carry rows shift by 2N columns (tile renaming); freed slots load the new rows ----
+        pd_static_for<0, RT>([&](auto RI) {
+            constexpr int rt = decltype(RI)::value;
+            const int slot = rt * 8 + q;
+            if (!bit(freem, slot)) {
+                if (l > 0) {
+#pragma unroll
+                    for (int ct = 0; ct < HT; ++ct) {
+                        c[rt][ct][0] = c[rt][ct + HT][0];
+                        c[rt][ct][1] = c[rt][ct + HT][1];
+                        c[rt][ct + HT][0] = 0.0;
+                        c[rt][ct + HT][1] = 0.0;
+                    }
+                }
+            } else {
+                const int idx = pd_popc(freem & below(slot));
+                if (!last) {  // continuity row `idx` of interface l  (_solve_for_coeffs.py:317-323)
+#pragma unroll
+                    for (int ct = 0; ct < CT; ++ct) {
+                        const int nb = ct / NT8, cc0 = (ct % NT8) * 8 + 2 * t;
+                        pd_d2 v = *reinterpret_cast<const pd_d2*>(Grow(l + (nb >> 1), idx, nb & 1) + cc0);
+                        if (nb == 0) {
+                            v.x *= E[cc0];
+                            v.y *= E[cc0 + 1];
+                        } else if (nb == 2) {
+                            v.x = -v.x;
+                            v.y = -v.y;
+                        } else if (nb == 3) {
+                            v.x *= -E[N + cc0];
+                            v.y *= -E[N + cc0 + 1];
+                        }
+                        c[rt][ct][0] = v.x;
+                        c[rt][ct][1] = v.y;
+                    }
+                } else if (idx < N) {  // bottom boundary row `idx`  (:163, :289-293)
+#pragma unroll
+                    for (int ct = 0; ct < HT; ++ct) {
+                        const int nb = ct / NT8, cc0 = (ct % NT8) * 8 + 2 * t;
+                        const double* g0 = Grow(l, idx, nb) + cc0;
+                        double v0 = g0[0], v1 = g0[1];
+                        if (has_bdrf)
+                            for (int j = 0; j < N; ++j) {
+                                const double* gj = Grow(l, N + j, nb) + cc0;
+                                v0 = fma(-R[idx * N + j], gj[0], v0);
+                                v1 = fma(-R[idx * N + j], gj[1], v1);
+                            }
+                        if (nb == 0) {
+                            v0 *= E[cc0];
+                            v1 *= E[cc0 + 1];
+                        }
+                        c[rt][ct][0] = v0;
+                        c[rt][ct][1] = v1;
+                        c[rt][ct + HT][0] = 0.0;
+                        c[rt][ct + HT][1] = 0.0;
+                    }
+                } else {  // unused slot of the last stage
+#pragma unroll
+                    for (int ct = 0; ct < CT; ++ct) c[rt][ct][0] = c[rt][ct][1] = 0.0;
+                }
+            }
+        });
+        // right-hand sides of the new rows  (:184-254)
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            const int slot = lane + 32 * r;
+            pj[r] = -1;
+            if (slot < NR && bit(freem, slot)) {
+                const int idx = pd_popc(freem & below(slot));
+                double v = 0.0;
+                if (!last) {
+                    if (beam) v = (Bc[(l + 1) * N2 + idx] - Bc[l * N2 + idx]) * att[l + 1];
+                    if (dthc)
+                        v += pd_thermal_at(dthc + (long)(l + 1) * A.Ns * N2, A.Ns, N2, idx, taus[l + 1]) -
+                             pd_thermal_at(dthc + (long)l * A.Ns * N2, A.Ns, N2, idx, taus[l + 1]);
+                } else if (idx < N) {
+                    v = have_b ? bpos[idx] : 0.0;
+                    if (dthc) {
+                        const double* dl = dthc + (long)l * A.Ns * N2;
+                        v -= pd_thermal_at(dl, A.Ns, N2, idx, taus[L]);
+                        if (has_bdrf)
+                            for (int j = 0; j < N; ++j) v = fma(R[idx * N + j], pd_thermal_at(dl, A.Ns, N2, N + j, taus[L]), v);
+                    }
+                    if (beam) {
+                        double s = -Bc[l * N2 + idx];
+                        if (has_bdrf) {
+                            const double* q0 = A.bdrf_q0 + ((A.bdrf_percol ? (long)b * A.NBDRF : 0) + m) * N;
+                            s += (mu0 * I0 / PD_PI) * q0[idx];
+                            for (int j = 0; j < N; ++j) s = fma(R[idx * N + j], Bc[l * N2 + N + j], s);
+                        }
+                        v = fma(s, att[L], v);
+                    }
+                }
+                rhs[r] = v;
+            }
+        }
+
+        // ---- elimination of the 2N columns of C_l in blocks of four ----
+        mask_t pivm = 0;
+        pd_static_for<0, NB>([&](auto KB) {
+            constexpr int kb = decltype(KB)::value;
+            constexpr int j0 = 4 * kb, ctJ = j0 / 8, t0 = (j0 % 8) / 2, ctmin = (j0 + 4) / 8;
+            // 1. publish the block's columns, pick up one row per lane
+            if ((t >> 1) == (t0 >> 1)) {
+#pragma unroll
+                for (int rt = 0; rt < RT; ++rt) {
+                    pd_d2 v2;
+                    v2.x = c[rt][ctJ][0];
+                    v2.y = c[rt][ctJ][1];
+                    *reinterpret_cast<pd_d2*>(blkV + (rt * 8 + q) * 4 + 2 * (t - t0)) = v2;
+                }
+            }
+            __syncwarp();
+            double v[RPL][4], g[RPL][4];
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                const int slot = lane + 32 * r;
+                pd_d2 lo, hi;
+                lo.x = lo.y = hi.x = hi.y = 0.0;
+                if (slot < NR) {
+                    lo = *reinterpret_cast<const pd_d2*>(blkV + slot * 4);
+                    hi = *reinterpret_cast<const pd_d2*>(blkV + slot * 4 + 2);
+                }
+                v[r][0] = lo.x; v[r][1] = lo.y; v[r][2] = hi.x; v[r][3] = hi.y;
+                g[r][0] = g[r][1] = g[r][2] = g[r][3] = 0.0;
+            }
+            // 2. four pivots, partial pivoting over the rows in play
+            int p[4];
+            pd_static_for<0, 4>([&](auto KI) {
+                constexpr int k = decltype(KI)::value;
+                unsigned kbest = 0u;
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) {
+                    const int slot = lane + 32 * r;
+                    const unsigned hi = (unsigned)__double2hiint(fabs(v[r][k]));
+                    const unsigned key = (slot < NR && bit(active, slot)) ? ((hi & ~63u) | (unsigned)(63 - slot)) : 0u;
+                    kbest = max(kbest, key);
+                }
+                const unsigned kall = __reduce_max_sync(FULL, kbest);
+                if ((kall & ~63u) == 0u) status |= PD_ST_ZERO_PIVOT;
+                const int ps = 63 - (int)(kall & 63u), pl = ps & 31, pr = ps >> 5;
+                p[k] = ps;
+                active &= ~((mask_t)1 << ps);
+                pivm |= (mask_t)1 << ps;
+                double pv[4], hg[4];
+#pragma unroll
+                for (int i = k; i < 4; ++i) {
+                    double src = v[0][i];
+                    if constexpr (RPL > 1) src = pr ? v[RPL - 1][i] : src;
+                    pv[i] = __shfl_sync(FULL, src, pl);
+                }
+#pragma unroll
+                for (int i = 0; i < k; ++i) {
+                    double src = g[0][i];
+                    if constexpr (RPL > 1) src = pr ? g[RPL - 1][i] : src;
+                    hg[i] = __shfl_sync(FULL, src, pl);
+                }
+                const double pinv = pd_rcp(pv[k]);
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) {
+                    const int slot = lane + 32 * r;
+                    const double f = v[r][k] * pinv;
+                    if (slot != ps) {
+#pragma unroll
+                        for (int i = k + 1; i < 4; ++i) v[r][i] = fma(-f, pv[i], v[r][i]);
+#pragma unroll
+                        for (int i = 0; i < k; ++i) g[r][i] = fma(-f, hg[i], g[r][i]);
+                        g[r][k] = f;
+                    } else {  // the pivot row is normalised; from now on it is an ordinary row with s = 0
+#pragma unroll
+                        for (int i = k + 1; i < 4; ++i) v[r][i] *= pinv;
+#pragma unroll
+                        for (int i = 0; i < k; ++i) g[r][i] *= pinv;
+                        g[r][k] = -pinv;
+                        pj[r] = j0 + k;
+                    }
+                }
+            });
+            const mask_t blockm = ((mask_t)1 << p[0]) | ((mask_t)1 << p[1]) | ((mask_t)1 << p[2]) | ((mask_t)1 << p[3]);
+            // 4. right-hand side
+            {
+                double rp[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    double src = rhs[0];
+                    if constexpr (RPL > 1) src = (p[k] >> 5) ? rhs[RPL - 1] : src;
+                    rp[k] = __shfl_sync(FULL, src, p[k] & 31);
+                }
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) {
+                    const int slot = lane + 32 * r;
+                    double s = bit(blockm, slot & (8 * (int)sizeof(mask_t) - 1)) ? 0.0 : rhs[r];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) s = fma(-g[r][k], rp[k], s);
+                    rhs[r] = s;
+                }
+            }
+            // 3. operands through shared memory, then the rank-4 update of every live tile
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                const int slot = lane + 32 * r;
+                if (slot < NR) {
+                    pd_d2 lo, hi;
+                    lo.x = -g[r][0]; lo.y = -g[r][1]; hi.x = -g[r][2]; hi.y = -g[r][3];
+                    *reinterpret_cast<pd_d2*>(blkA + slot * 4) = lo;
+                    *reinterpret_cast<pd_d2*>(blkA + slot * 4 + 2) = hi;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int rtk = p[k] >> 3, qk = p[k] & 7;  // warp-uniform
+                pd_static_for<0, RT>([&](auto RI) {
+                    constexpr int rt = decltype(RI)::value;
+                    if (rtk == rt && q == qk) {
+#pragma unroll
+                        for (int ct = ctmin; ct < CT; ++ct) {
+                            pd_d2 v2;
+                            v2.x = c[rt][ct][0];
+                            v2.y = c[rt][ct][1];
+                            *reinterpret_cast<pd_d2*>(prow + k * PS + ct * 8 + 2 * t) = v2;
+                        }
+                    }
+                });
+            }
+            __syncwarp();
+            double af[RT], bf[CT];
+#pragma unroll
+            for (int rt = 0; rt < RT; ++rt) af[rt] = blkA[(rt * 8 + q) * 4 + t];
+#pragma unroll
+            for (int ct = ctmin; ct < CT; ++ct) bf[ct] = prow[t * PS + ct * 8 + q];
+#pragma unroll
+            for (int rt = 0; rt < RT; ++rt) {
+                if (bit(blockm, rt * 8 + q)) {
+#pragma unroll
+                    for (int ct = ctmin; ct < CT; ++ct) c[rt][ct][0] = c[rt][ct][1] = 0.0;
+                }
+#pragma unroll
+                for (int ct = ctmin; ct < CT; ++ct) pd_dmma(c[rt][ct][0], c[rt][ct][1], af[rt], bf[ct]);
+            }
+        });
+
+        // ---- the pivot row of column j holds row j of U11^-1 [U12 | y] ----
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            const int slot = lane + 32 * r;
+            if (slot < NR) colOf[slot] = pj[r];
+        }
+        __syncwarp();
+        double* hl = hist + (long)l * F::HIST_PER_LAYER;
+        if (!last) {
+#pragma unroll
+            for (int rt = 0; rt < RT; ++rt) {
+                const int j = colOf[rt * 8 + q];
+                if (j >= 0) {
+#pragma unroll
+                    for (int ct = HT; ct < CT; ++ct) {
+                        pd_d2 v2;
+                        v2.x = -c[rt][ct][0];
+                        v2.y = -c[rt][ct][1];
+                        *reinterpret_cast<pd_d2*>(hl + (long)j * N2 + (ct - HT) * 8 + 2 * t) = v2;
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RPL; ++r)
+                if (pj[r] >= 0) hl[N2 * N2 + pj[r]] = rhs[r];
+        } else {
+#pragma unroll
+            for (int r = 0; r < RPL; ++r)
+                if (pj[r] >= 0) xs[pj[r]] = rhs[r];
+        }
+        freem = pivm;
+        __syncwarp();
+    }
+
+    // ---- back sweep: x_l = z_l + M_l x_{l+1}; HL lanes per row ----
+    constexpr int HL = 32 / N2, SEG = N2 / HL;
+    const int jr = lane / HL, hh = lane % HL;
+    double* Cout = A.C + sys * L * N2;
+    if (hh == 0) Cout[(long)(L - 1) * N2 + jr] = xs[jr];
+    double mrow[SEG], zj = 0.0;
+    auto load_hist = [&](int l) {
+        const double* h = hist + (long)l * F::HIST_PER_LAYER + (long)jr * N2 + hh * SEG;
+#pragma unroll
+        for (int cc = 0; cc < SEG; cc += 2) {
+            const pd_d2 v2 = *reinterpret_cast<const pd_d2*>(h + cc);
+            mrow[cc] = v2.x;
+            mrow[cc + 1] = v2.y;
+        }
+        zj = (hh == 0) ? hist[(long)l * F::HIST_PER_LAYER + N2 * N2 + jr] : 0.0;
+    };
+    if (L >= 2) load_hist(L - 2);
+    for (int l = L - 2; l >= 0; --l) {
+        double s0 = zj, s1 = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < SEG; cc += 2) {
+            const pd_d2 xv = *reinterpret_cast<const pd_d2*>(xs + hh * SEG + cc);
+            s0 = fma(mrow[cc], xv.x, s0);
+            s1 = fma(mrow[cc + 1], xv.y, s1);
+        }
+        double s = s0 + s1;
+        if (l > 0) load_hist(l - 1);  // independent of x: in flight across the barrier
+        if constexpr (HL == 2) s += __shfl_xor_sync(FULL, s, 1);
+        __syncwarp();
+        if (hh == 0) {
+            xs[jr] = s;
+            Cout[(long)l * N2 + jr] = s;
+        }
+        __syncwarp();
+    }
+    if (status && lane == 0) atomicOr(A.status + b, status);
+}
+
+#endif  // __CUDACC__
