@@ -6,7 +6,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "libpydisort_b200.so")
+LIB_PATH = os.environ.get("PD_LIB_PATH") or os.path.join(HERE, "libpydisort_b200.so")  # override: tuning experiments only
 SOURCES = ["pd_api.cu", "pd_kernel_a.cu", "pd_kernel_b.cu", "pd_kernel_eval.cu"]
 
 
@@ -16,8 +16,8 @@ def _headers():
 
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC"]
-BUILD_DIR = os.path.join(HERE, "build")
+              "-Xcompiler", "-fPIC"] + os.environ.get("PD_NVCC_EXTRA", "").split()  # -D tuning switches for experiments
+BUILD_DIR = os.environ.get("PD_BUILD_DIR") or os.path.join(HERE, "build")
 
 
 class pd_config(ctypes.Structure):

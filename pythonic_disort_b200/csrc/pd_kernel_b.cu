@@ -251,7 +251,7 @@ static StageBPlan plan_mma(int B, int NF, int L) {
     p.sys_doubles = PdStageBMma<N>::smem_doubles(L);
     p.wpb = 4;
     p.smem = (size_t)p.sys_doubles * 8 * p.wpb;
-    int ctas_per_sm = (int)(PD_SMEM_BUDGET / p.smem);
+    int ctas_per_sm = (int)((PD_SMEM_MAX_CTA + 1024) / (p.smem + 1024));  // refined by the occupancy query below
     if (ctas_per_sm * p.wpb > 32) ctas_per_sm = 32 / p.wpb;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     int occ = 0;

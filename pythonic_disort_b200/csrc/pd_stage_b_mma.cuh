@@ -14,8 +14,8 @@
 //   1. the live tiles are stored to the mirror; every lane picks up the four J-values of "its" row (one lane per
 //      row; the right-hand side lives in this layout and is eliminated like a fifth column);
 //   2. the four pivots are found one after the other with partial pivoting over the rows still in play (32-bit
-//      magnitude key + REDUX.MAX; the pivot lane publishes its four values, its multipliers, its right-hand side
-//      and -1/pivot in one small packet).  The elimination is Gauss-Jordan without normalisation (earlier pivot
+//      magnitude key + REDUX.MAX; the pivot lane's block values, multipliers, right-hand side and -1/pivot are
+//      broadcast with shuffles -- shorter than a shared-memory round trip, and this chain is what bounds the kernel).  The elimination is Gauss-Jordan without normalisation (earlier pivot
 //      rows keep being reduced) and is applied to the four block columns only; every row accumulates its multipliers
 //      g with respect to the ORIGINAL four pivot rows:   new_row_i = row_i + sum_k g[i][k] * row_{p_k};
 //   3. A = g (3N x 4, through shared memory) and B = the four pivot rows (4 x 4N, from the mirror) are loaded in
@@ -31,16 +31,23 @@
 
 #if defined(__CUDACC__)
 
+#ifndef PD_MMA_BCAST_SHFL
+#define PD_MMA_BCAST_SHFL 0  // pivot packet by warp shuffles (1) or through shared memory (0)
+#endif
+#ifndef PD_MMA_PF
+#define PD_MMA_PF 2          // layers of history in flight in the back sweep
+#endif
+
 template <int N>
 struct PdStageBMma {
     static_assert(N % 8 == 0 && N <= 16, "tensor-core stage B: N = 8 or 16");
     static constexpr int N2 = 2 * N, NR = 3 * N, RC = 4 * N, RT = NR / 8, CT = RC / 8, HT = CT / 2, NB = N2 / 4;
     static constexpr int RPL = (NR + 31) / 32;  // rows per lane in the one-lane-per-row layout
     static constexpr int NT8 = N / 8;           // tiles per N columns
-    static constexpr int BLK = NR * 4;          // block columns / multipliers: [NR][4]
-    static constexpr int PS = RC + 4;           // stride of a published pivot row: 4 (mod 16) doubles, so that the
-                                                // operand loads of a half warp touch 16 distinct bank pairs
-    static constexpr int SMEM_FIXED = 2 * BLK + 4 * PS + N * N + N2 + NR / 2;
+    static constexpr int RS = RC + 8;           // row stride of the mirror: 8 (mod 16) doubles, so that the 128-bit tile
+                                                // stores of a quarter warp (two rows) fall into disjoint bank halves
+    static constexpr int MIRROR = NR * RS, BLK = NR * 4, PKT = 2 * 8;
+    static constexpr int SMEM_FIXED = MIRROR + BLK + PKT + N * N + N2 + NR + NR / 2;
     PD_HD static int smem_doubles(int L) { return (SMEM_FIXED + L * N + L + 1 + 1) & ~1; }
     static constexpr long HIST_PER_LAYER = (long)N2 * N2 + N2;  // M_l [2N][2N] row-major, z_l [2N]
     using mask_t = typename std::conditional<(NR > 32), unsigned long long, unsigned>::type;
@@ -48,6 +55,16 @@ struct PdStageBMma {
 
 __device__ __forceinline__ int pd_popc(unsigned v) { return __popc(v); }
 __device__ __forceinline__ int pd_popc(unsigned long long v) { return __popcll(v); }
+
+// 1/x to about an ulp with a three-deep dependent chain after the hardware seed (cubic correction: e + e^2)
+__device__ __forceinline__ double pd_rcp3(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    r = fma(r, fma(e, e, e), r);
+    const double e2 = fma(-x, r, 1.0);  // off the chain when the seed is good to 2^-20; keeps full accuracy if it is not
+    return fma(r, e2, r);
+}
 
 // D = A (8x4, row) * B (4x8, col) + D on the FP64 tensor cores
 __device__ __forceinline__ void pd_dmma(double& c0, double& c1, double a, double b) {
@@ -58,18 +75,19 @@ template <int N>
 __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, double* hist) {
     using F = PdStageBMma<N>;
     using mask_t = typename F::mask_t;
-    constexpr int N2 = F::N2, NR = F::NR, RC = F::RC, RT = F::RT, CT = F::CT, HT = F::HT, NB = F::NB, RPL = F::RPL;
-    constexpr int NT8 = F::NT8, PS = F::PS;
+    constexpr int N2 = F::N2, NR = F::NR, RT = F::RT, CT = F::CT, HT = F::HT, NB = F::NB, RPL = F::RPL;
+    constexpr int NT8 = F::NT8, RS = F::RS;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, q = lane >> 2, t = lane & 3;
     const int L = A.L;
-    double* blkV = sm;                   // [NR][4] the block's four columns, one row per slot
-    double* blkA = blkV + F::BLK;        // [NR][4] A operand: -g
-    double* prow = blkA + F::BLK;        // [4][PS] the block's four pivot rows (B operand)
-    double* R = prow + 4 * PS;           // [N][N]
+    double* mir = sm;                    // [NR][RS] mirror of the panel
+    double* blkA = mir + F::MIRROR;      // [NR][4] A operand: the multipliers g
+    double* pkt = blkA + F::BLK;         // [2][8] pivot packet, double buffered
+    double* R = pkt + F::PKT;            // [N][N]
     double* xs = R + N * N;              // [2N]
-    int* colOf = reinterpret_cast<int*>(xs + N2);  // [NR] pivot column of a row slot in this stage, -1: none
-    double* Eall = xs + N2 + NR / 2;     // [L][N]  exp(-k_l dtau*_l)
+    double* npOf = xs + N2;              // [NR] -1/pivot of a row slot that was a pivot row in this stage
+    int* colOf = reinterpret_cast<int*>(npOf + NR);  // [NR] its pivot column, -1: none
+    double* Eall = npOf + NR + NR / 2;   // [L][N]  exp(-k_l dtau*_l)
     double* att = Eall + (long)L * N;    // [L+1]   exp(-tau*_l / mu0)
 
     const long sys = (long)b * A.NF + m;
@@ -85,7 +103,6 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
     const bool have_b = (m == 0) || (A.NFb > 1);
     const double* bpos = A.bpos + ((long)b * A.NFb + (A.NFb > 1 ? m : 0)) * N;
     const double* bneg = A.bneg + ((long)b * A.NFb + (A.NFb > 1 ? m : 0)) * N;
-    int status = 0;
 
     auto Grow = [&](int l, int r, int half) -> const double* {  // the N entries G_l[r][half*N .. half*N+N)
         const int rb = r >= N;
@@ -109,7 +126,9 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
 
     double c[RT][CT][2];  // accumulator tiles: row slot rt*8 + q, columns ct*8 + 2t + {0, 1}
     double rhs[RPL];      // right-hand side of row slot lane + 32 r
-    int pj[RPL];          // pivot column of that slot in the current stage (-1: none)
+    double mynp[RPL];     // -1/pivot of that slot if it was a pivot row in the current stage
+    int pj[RPL];          // its pivot column (-1: none)
+    bool act[RPL];        // still a pivot candidate
 #pragma unroll
     for (int rt = 0; rt < RT; ++rt)
 #pragma unroll
@@ -141,31 +160,23 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
             if (dthc) v -= pd_thermal_at(dthc, A.Ns, N2, N + slot, taus[0]);
         }
         rhs[r] = v;
+        mynp[r] = 0.0;
         pj[r] = -1;
     }
     mask_t freem = ALL & ~below(N);  // slots that take new rows at the start of the coming stage
+    unsigned kmin = 0xffffffffu;     // smallest pivot key seen (zero-pivot detection)
 
     for (int l = 0; l < L; ++l) {
         const bool last = (l == L - 1);
         const double* E = Eall + (long)l * N;  // E[c]: layer l, E[N + c]: layer l + 1
-        if (l + 2 < L && lane * 16 < 2 * N * N)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(Gc + ((long)(l + 2) * 2) * N * N + lane * 16));
-
-        // ---- rows in play: the carry (never a pivot) plus the new rows ----
-        mask_t active;
-        if (!last) {
-            active = ALL;
-        } else {  // only N new rows: the first N free slots
-            mask_t fm = freem, firstN = 0;
-            for (int i = 0; i < N; ++i) {
-                const mask_t low = fm & (~fm + 1);
-                firstN |= low;
-                fm ^= low;
-            }
-            active = (ALL & ~freem) | firstN;
+        if (lane * 16 < 2 * N * N) {  // G two stages ahead into L1, six stages ahead into L2; the beam vector next to it
+            if (l + 2 < L) asm volatile("prefetch.global.L1 [%0];" ::"l"(Gc + ((long)(l + 2) * 2) * N * N + lane * 16));
+            if (l + 6 < L) asm volatile("prefetch.global.L2 [%0];" ::"l"(Gc + ((long)(l + 6) * 2) * N * N + lane * 16));
+        } else if (Bc && lane == 31 && l + 3 < L) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(Bc + (long)(l + 3) * N2));
         }
 
-        // ---- carry rows shift by 2N columns (tile renaming); freed slots load the new rows ----
+        // ---- carry rows shift by 2N columns; freed slots load the new rows ----
         pd_static_for<0, RT>([&](auto RI) {
             constexpr int rt = decltype(RI)::value;
             const int slot = rt * 8 + q;
@@ -226,11 +237,12 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
                 }
             }
         });
-        // right-hand sides of the new rows  (:184-254)
+        // right-hand sides of the new rows  (:184-254); which rows are in play
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
             const int slot = lane + 32 * r;
             pj[r] = -1;
+            act[r] = slot < NR;
             if (slot < NR && bit(freem, slot)) {
                 const int idx = pd_popc(freem & below(slot));
                 double v = 0.0;
@@ -256,26 +268,27 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
                         }
                         v = fma(s, att[L], v);
                     }
+                } else {
+                    act[r] = false;  // the last stage has only N new rows
                 }
                 rhs[r] = v;
             }
         }
 
         // ---- elimination of the 2N columns of C_l in blocks of four ----
-        mask_t pivm = 0;
         pd_static_for<0, NB>([&](auto KB) {
             constexpr int kb = decltype(KB)::value;
-            constexpr int j0 = 4 * kb, ctJ = j0 / 8, t0 = (j0 % 8) / 2, ctmin = (j0 + 4) / 8;
-            // 1. publish the block's columns, pick up one row per lane
-            if ((t >> 1) == (t0 >> 1)) {
+            constexpr int j0 = 4 * kb, ctlive = j0 / 8, ctmin = (j0 + 4) / 8;
+            // 1. live tiles to the mirror; one row per lane picks up the block's columns
 #pragma unroll
-                for (int rt = 0; rt < RT; ++rt) {
+            for (int rt = 0; rt < RT; ++rt)
+#pragma unroll
+                for (int ct = ctlive; ct < CT; ++ct) {
                     pd_d2 v2;
-                    v2.x = c[rt][ctJ][0];
-                    v2.y = c[rt][ctJ][1];
-                    *reinterpret_cast<pd_d2*>(blkV + (rt * 8 + q) * 4 + 2 * (t - t0)) = v2;
+                    v2.x = c[rt][ct][0];
+                    v2.y = c[rt][ct][1];
+                    *reinterpret_cast<pd_d2*>(mir + (rt * 8 + q) * RS + ct * 8 + 2 * t) = v2;
                 }
-            }
             __syncwarp();
             double v[RPL][4], g[RPL][4];
 #pragma unroll
@@ -284,132 +297,121 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
                 pd_d2 lo, hi;
                 lo.x = lo.y = hi.x = hi.y = 0.0;
                 if (slot < NR) {
-                    lo = *reinterpret_cast<const pd_d2*>(blkV + slot * 4);
-                    hi = *reinterpret_cast<const pd_d2*>(blkV + slot * 4 + 2);
+                    lo = *reinterpret_cast<const pd_d2*>(mir + slot * RS + j0);
+                    hi = *reinterpret_cast<const pd_d2*>(mir + slot * RS + j0 + 2);
                 }
                 v[r][0] = lo.x; v[r][1] = lo.y; v[r][2] = hi.x; v[r][3] = hi.y;
-                g[r][0] = g[r][1] = g[r][2] = g[r][3] = 0.0;
             }
-            // 2. four pivots, partial pivoting over the rows in play
+            // 2. four pivots, partial pivoting over the rows in play; g: new_row = row + sum_k g[k] * (original pivot row k)
             int p[4];
             pd_static_for<0, 4>([&](auto KI) {
                 constexpr int k = decltype(KI)::value;
-                unsigned kbest = 0u;
+                unsigned key[RPL], kbest = 0u;
 #pragma unroll
                 for (int r = 0; r < RPL; ++r) {
                     const int slot = lane + 32 * r;
                     const unsigned hi = (unsigned)__double2hiint(fabs(v[r][k]));
-                    const unsigned key = (slot < NR && bit(active, slot)) ? ((hi & ~63u) | (unsigned)(63 - slot)) : 0u;
-                    kbest = max(kbest, key);
+                    key[r] = act[r] ? ((hi & ~63u) | (unsigned)(63 - slot)) : 0u;
+                    kbest = max(kbest, key[r]);
                 }
+                int mr = 0;  // register row of this lane's candidate
+                if constexpr (RPL > 1) mr = (key[RPL - 1] > key[0]) ? RPL - 1 : 0;
+                // this lane's packet in case it wins: multipliers g[< k], block values v[> k], right-hand side, -1/candidate
+                // (the reciprocal is computed by every lane in the shadow of the reduction)
+                double pk[4], prhs, cinv;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (i < k) pk[i] = (RPL > 1 && mr) ? g[RPL - 1][i] : g[0][i];
+                    else pk[i] = (RPL > 1 && mr) ? v[RPL - 1][i] : v[0][i];
+                }
+                prhs = (RPL > 1 && mr) ? rhs[RPL - 1] : rhs[0];
+                cinv = pd_rcp3(-pk[k]);
                 const unsigned kall = __reduce_max_sync(FULL, kbest);
-                if ((kall & ~63u) == 0u) status |= PD_ST_ZERO_PIVOT;
-                const int ps = 63 - (int)(kall & 63u), pl = ps & 31, pr = ps >> 5;
-                p[k] = ps;
-                active &= ~((mask_t)1 << ps);
-                pivm |= (mask_t)1 << ps;
-                double pv[4], hg[4];
+                kmin = min(kmin, kall);
+                p[k] = 63 - (int)(kall & 63u);
+                double x[4], xr, npinv;
+#if PD_MMA_BCAST_SHFL
+                const int pl = p[k] & 31;
 #pragma unroll
-                for (int i = k; i < 4; ++i) {
-                    double src = v[0][i];
-                    if constexpr (RPL > 1) src = pr ? v[RPL - 1][i] : src;
-                    pv[i] = __shfl_sync(FULL, src, pl);
+                for (int i = 0; i < 4; ++i)
+                    if (i != k) x[i] = __shfl_sync(FULL, pk[i], pl);
+                xr = __shfl_sync(FULL, prhs, pl);
+                npinv = __shfl_sync(FULL, cinv, pl);
+#else
+                {
+                    double* pb = pkt + (k & 1) * 8;
+                    if (kbest == kall) {  // keys are unique: this lane owns the pivot row
+                        pd_d2 a0, a1, a2;
+                        a0.x = pk[0]; a0.y = pk[1]; a1.x = pk[2]; a1.y = pk[3]; a2.x = prhs; a2.y = cinv;
+                        *reinterpret_cast<pd_d2*>(pb) = a0;
+                        *reinterpret_cast<pd_d2*>(pb + 2) = a1;
+                        *reinterpret_cast<pd_d2*>(pb + 4) = a2;
+                    }
+                    __syncwarp();
+                    const pd_d2 x01 = *reinterpret_cast<const pd_d2*>(pb), x23 = *reinterpret_cast<const pd_d2*>(pb + 2);
+                    const pd_d2 x45 = *reinterpret_cast<const pd_d2*>(pb + 4);
+                    x[0] = x01.x; x[1] = x01.y; x[2] = x23.x; x[3] = x23.y;
+                    xr = x45.x;
+                    npinv = x45.y;
                 }
-#pragma unroll
-                for (int i = 0; i < k; ++i) {
-                    double src = g[0][i];
-                    if constexpr (RPL > 1) src = pr ? g[RPL - 1][i] : src;
-                    hg[i] = __shfl_sync(FULL, src, pl);
-                }
-                const double pinv = pd_rcp(pv[k]);
+#endif
 #pragma unroll
                 for (int r = 0; r < RPL; ++r) {
-                    const int slot = lane + 32 * r;
-                    const double f = v[r][k] * pinv;
-                    if (slot != ps) {
+                    const bool mine = key[r] == kall;
+                    const double f = mine ? 0.0 : v[r][k] * npinv;  // row += f * (pivot row)
 #pragma unroll
-                        for (int i = k + 1; i < 4; ++i) v[r][i] = fma(-f, pv[i], v[r][i]);
+                    for (int i = k + 1; i < 4; ++i) v[r][i] = fma(f, x[i], v[r][i]);
+                    rhs[r] = fma(f, xr, rhs[r]);
 #pragma unroll
-                        for (int i = 0; i < k; ++i) g[r][i] = fma(-f, hg[i], g[r][i]);
-                        g[r][k] = f;
-                    } else {  // the pivot row is normalised; from now on it is an ordinary row with s = 0
-#pragma unroll
-                        for (int i = k + 1; i < 4; ++i) v[r][i] *= pinv;
-#pragma unroll
-                        for (int i = 0; i < k; ++i) g[r][i] *= pinv;
-                        g[r][k] = -pinv;
+                    for (int i = 0; i < k; ++i) g[r][i] = fma(f, x[i], g[r][i]);
+                    g[r][k] = f;
+                    if (mine) {
+                        act[r] = false;
                         pj[r] = j0 + k;
+                        mynp[r] = npinv;
                     }
                 }
             });
-            const mask_t blockm = ((mask_t)1 << p[0]) | ((mask_t)1 << p[1]) | ((mask_t)1 << p[2]) | ((mask_t)1 << p[3]);
-            // 4. right-hand side
-            {
-                double rp[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    double src = rhs[0];
-                    if constexpr (RPL > 1) src = (p[k] >> 5) ? rhs[RPL - 1] : src;
-                    rp[k] = __shfl_sync(FULL, src, p[k] & 31);
-                }
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) {
-                    const int slot = lane + 32 * r;
-                    double s = bit(blockm, slot & (8 * (int)sizeof(mask_t) - 1)) ? 0.0 : rhs[r];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) s = fma(-g[r][k], rp[k], s);
-                    rhs[r] = s;
-                }
-            }
-            // 3. operands through shared memory, then the rank-4 update of every live tile
+            // 3. operands, then the rank-4 update of every live tile
 #pragma unroll
             for (int r = 0; r < RPL; ++r) {
                 const int slot = lane + 32 * r;
                 if (slot < NR) {
                     pd_d2 lo, hi;
-                    lo.x = -g[r][0]; lo.y = -g[r][1]; hi.x = -g[r][2]; hi.y = -g[r][3];
+                    lo.x = g[r][0]; lo.y = g[r][1]; hi.x = g[r][2]; hi.y = g[r][3];
                     *reinterpret_cast<pd_d2*>(blkA + slot * 4) = lo;
                     *reinterpret_cast<pd_d2*>(blkA + slot * 4 + 2) = hi;
                 }
             }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int rtk = p[k] >> 3, qk = p[k] & 7;  // warp-uniform
-                pd_static_for<0, RT>([&](auto RI) {
-                    constexpr int rt = decltype(RI)::value;
-                    if (rtk == rt && q == qk) {
-#pragma unroll
-                        for (int ct = ctmin; ct < CT; ++ct) {
-                            pd_d2 v2;
-                            v2.x = c[rt][ct][0];
-                            v2.y = c[rt][ct][1];
-                            *reinterpret_cast<pd_d2*>(prow + k * PS + ct * 8 + 2 * t) = v2;
-                        }
-                    }
-                });
-            }
             __syncwarp();
+            const int pt = (t & 2) ? ((t & 1) ? p[3] : p[2]) : ((t & 1) ? p[1] : p[0]);
+            const double* brow = mir + pt * RS + q;
             double af[RT], bf[CT];
 #pragma unroll
             for (int rt = 0; rt < RT; ++rt) af[rt] = blkA[(rt * 8 + q) * 4 + t];
 #pragma unroll
-            for (int ct = ctmin; ct < CT; ++ct) bf[ct] = prow[t * PS + ct * 8 + q];
+            for (int ct = ctmin; ct < CT; ++ct) bf[ct] = brow[ct * 8];
+            __syncwarp();  // the mirror is rewritten at the start of the next block
 #pragma unroll
-            for (int rt = 0; rt < RT; ++rt) {
-                if (bit(blockm, rt * 8 + q)) {
-#pragma unroll
-                    for (int ct = ctmin; ct < CT; ++ct) c[rt][ct][0] = c[rt][ct][1] = 0.0;
-                }
+            for (int rt = 0; rt < RT; ++rt)
 #pragma unroll
                 for (int ct = ctmin; ct < CT; ++ct) pd_dmma(c[rt][ct][0], c[rt][ct][1], af[rt], bf[ct]);
-            }
         });
 
-        // ---- the pivot row of column j holds row j of U11^-1 [U12 | y] ----
+        // ---- the pivot row of column j holds pivot_j * (row j of U11^-1 [U12 | y]) ----
+        mask_t pivm;
+        {
+            const unsigned b0 = __ballot_sync(FULL, pj[0] >= 0);
+            pivm = (mask_t)b0;
+            if constexpr (RPL > 1) pivm |= (mask_t)__ballot_sync(FULL, pj[RPL - 1] >= 0) << 32 * (RPL - 1);
+        }
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
             const int slot = lane + 32 * r;
-            if (slot < NR) colOf[slot] = pj[r];
+            if (slot < NR) {
+                colOf[slot] = pj[r];
+                npOf[slot] = mynp[r];
+            }
         }
         __syncwarp();
         double* hl = hist + (long)l * F::HIST_PER_LAYER;
@@ -418,22 +420,23 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
             for (int rt = 0; rt < RT; ++rt) {
                 const int j = colOf[rt * 8 + q];
                 if (j >= 0) {
+                    const double np = npOf[rt * 8 + q];
 #pragma unroll
                     for (int ct = HT; ct < CT; ++ct) {
                         pd_d2 v2;
-                        v2.x = -c[rt][ct][0];
-                        v2.y = -c[rt][ct][1];
+                        v2.x = c[rt][ct][0] * np;
+                        v2.y = c[rt][ct][1] * np;
                         *reinterpret_cast<pd_d2*>(hl + (long)j * N2 + (ct - HT) * 8 + 2 * t) = v2;
                     }
                 }
             }
 #pragma unroll
             for (int r = 0; r < RPL; ++r)
-                if (pj[r] >= 0) hl[N2 * N2 + pj[r]] = rhs[r];
+                if (pj[r] >= 0) hl[N2 * N2 + pj[r]] = -rhs[r] * mynp[r];
         } else {
 #pragma unroll
             for (int r = 0; r < RPL; ++r)
-                if (pj[r] >= 0) xs[pj[r]] = rhs[r];
+                if (pj[r] >= 0) xs[pj[r]] = -rhs[r] * mynp[r];
         }
         freem = pivm;
         __syncwarp();
@@ -444,37 +447,49 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
     const int jr = lane / HL, hh = lane % HL;
     double* Cout = A.C + sys * L * N2;
     if (hh == 0) Cout[(long)(L - 1) * N2 + jr] = xs[jr];
-    double mrow[SEG], zj = 0.0;
-    auto load_hist = [&](int l) {
-        const double* h = hist + (long)l * F::HIST_PER_LAYER + (long)jr * N2 + hh * SEG;
+    constexpr int PF = PD_MMA_PF;  // layers of history in flight: the loads do not depend on x
+    double mrow[PF][SEG], zj[PF];
+    const double* hbase = hist + (long)jr * N2 + hh * SEG;
+    for (int l0 = L - 2; l0 >= 0; l0 -= PF) {
 #pragma unroll
-        for (int cc = 0; cc < SEG; cc += 2) {
-            const pd_d2 v2 = *reinterpret_cast<const pd_d2*>(h + cc);
-            mrow[cc] = v2.x;
-            mrow[cc + 1] = v2.y;
-        }
-        zj = (hh == 0) ? hist[(long)l * F::HIST_PER_LAYER + N2 * N2 + jr] : 0.0;
-    };
-    if (L >= 2) load_hist(L - 2);
-    for (int l = L - 2; l >= 0; --l) {
-        double s0 = zj, s1 = 0.0;
+        for (int u = 0; u < PF; ++u) {
+            const int l = l0 - u;
+            if (l >= 0) {
+                const double* h = hbase + (long)l * F::HIST_PER_LAYER;
 #pragma unroll
-        for (int cc = 0; cc < SEG; cc += 2) {
-            const pd_d2 xv = *reinterpret_cast<const pd_d2*>(xs + hh * SEG + cc);
-            s0 = fma(mrow[cc], xv.x, s0);
-            s1 = fma(mrow[cc + 1], xv.y, s1);
+                for (int cc = 0; cc < SEG; cc += 2) {
+                    const pd_d2 v2 = *reinterpret_cast<const pd_d2*>(h + cc);
+                    mrow[u][cc] = v2.x;
+                    mrow[u][cc + 1] = v2.y;
+                }
+                zj[u] = (hh == 0) ? hist[(long)l * F::HIST_PER_LAYER + N2 * N2 + jr] : 0.0;
+                if (l - 2 * PF >= 0)  // the chunk after next: from HBM into L2
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(h - 2L * PF * F::HIST_PER_LAYER));
+            }
         }
-        double s = s0 + s1;
-        if (l > 0) load_hist(l - 1);  // independent of x: in flight across the barrier
-        if constexpr (HL == 2) s += __shfl_xor_sync(FULL, s, 1);
-        __syncwarp();
-        if (hh == 0) {
-            xs[jr] = s;
-            Cout[(long)l * N2 + jr] = s;
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int l = l0 - u;
+            if (l >= 0) {
+                double s0 = zj[u], s1 = 0.0;
+#pragma unroll
+                for (int cc = 0; cc < SEG; cc += 2) {
+                    const pd_d2 xv = *reinterpret_cast<const pd_d2*>(xs + hh * SEG + cc);
+                    s0 = fma(mrow[u][cc], xv.x, s0);
+                    s1 = fma(mrow[u][cc + 1], xv.y, s1);
+                }
+                double s = s0 + s1;
+                if constexpr (HL == 2) s += __shfl_xor_sync(FULL, s, 1);
+                __syncwarp();
+                if (hh == 0) {
+                    xs[jr] = s;
+                    Cout[(long)l * N2 + jr] = s;
+                }
+                __syncwarp();
+            }
         }
-        __syncwarp();
     }
-    if (status && lane == 0) atomicOr(A.status + b, status);
+    if ((kmin & ~63u) == 0u && lane == 0) atomicOr(A.status + b, PD_ST_ZERO_PIVOT);
 }
 
 #endif  // __CUDACC__
