@@ -42,7 +42,7 @@ WORKLOADS = {
                     desc="shortwave ensemble, only_flux=True; fluxes at 61 levels"),
     "lw": dict(ens="lw", columns=1048576, desc="longwave ensemble: 60 layers, NQuad=8, thermal source, flux-only"),
     "ha": dict(ens="ha", columns=16384, desc="high-accuracy: 100 layers, NQuad=32, NFourier=32, Hapke BDRF, "
-               "intensities at 101 levels x 32 mu x 5 phi"),
+               "intensities at 101 levels x 6 user polar angles (mu = +-0.1, +-0.5, +-0.9; interpolate() on the device) x 5 phi"),
 }
 
 
@@ -84,7 +84,7 @@ def _cpu_worker(job):
     from oracle import disort_oracle
     from pythonic_disort_b200 import synthetic
     ens = make_inputs(name, ncol, first, only_flux)
-    synthetic.run_reference_like(disort_oracle.pydisort, ens)
+    synthetic.run_reference_like(disort_oracle.pydisort, ens, at_user_mu=True)
     return ncol
 
 
@@ -193,6 +193,7 @@ def run_gpu(args):
     dev_tau = as_dev(ens["tau_eval"])
     phi = ens["phi_eval"]
     phi_dev = torch.as_tensor(phi, device=dev) if phi is not None else None
+    mu_user = ens.get("mu_user")  # config 5: intensities at user polar angles (row f1)
 
     def step(a, kw, tau_eval, to_host):
         """The hot path over all columns, chunk by chunk; returns bytes copied (h2d, d2h)."""
@@ -212,7 +213,10 @@ def run_gpu(args):
                 out = pd.pydisort(*ca, **ck)
                 Fp = out[1](te)
                 Fm, Fd = out[2](te)
-                uu = out[4](te, phi if to_host else phi_dev) if want_u else None
+                if want_u and mu_user is not None:
+                    uu = pd.subroutines.interpolate(out[4])(mu_user, te, phi if to_host else phi_dev)
+                else:
+                    uu = out[4](te, phi if to_host else phi_dev) if want_u else None
             if to_host:  # host inputs -> the API returned NumPy arrays (device->host copies already done)
                 assert isinstance(Fp, np.ndarray)
                 d2h += (Fp.size + Fm.size + Fd.size + (uu.size if want_u else 0)) * 8
@@ -309,9 +313,8 @@ def run_gpu(args):
     item = NF * cfgL
     bytes_k = {"solve_eigen": item * (NLeg + 1) * 8 + item * (2 * N * N + N + 2 * N) * 8,
                "solve_bc": item * (2 * N * N + N + 2 * N) * 8 + item * 2 * N * 8}[dom]
-    fastN = N in (4, 8)
-    kname = {"solve_eigen": "k_stage_a_sym" if fastN else "k_stage_a",
-             "solve_bc": "k_stage_b_reg" if fastN else ("k_stage_b_fast" if N == 16 else "k_stage_b")}[dom]
+    kname = {"solve_eigen": "k_stage_a_sym" if N in (4, 8) else "k_stage_a",
+             "solve_bc": "k_stage_b_mma" if N in (8, 16) else ("k_stage_b_r3" if N == 4 else "k_stage_b")}[dom]
     # DRAM bytes per column of that kernel from the committed ncu capture (profiles/r1_traffic.json), if any
     traffic = None
     try:

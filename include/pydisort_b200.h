@@ -175,6 +175,15 @@ int pd_eval_u(const pd_config* cfg, const pd_state* st, const double* tau_q, int
               const double* omega_s, const double* wleg,
               double* u, double* ulast, void* stream);
 
+/* Interpolation of u or u0 from the quadrature streams to user polar angles
+ * (PythonicDISORT.subroutines.interpolate, subroutines.py:614-705: barycentric
+ * interpolation, separately per hemisphere).  The interpolation is linear in the
+ * stream values, so the caller passes it as a weight matrix wts[nmu][2N] (row o:
+ * barycentric weights of the N streams of the hemisphere of mu_o, zeros for the
+ * other hemisphere) and the kernel contracts the stream axis:
+ *   out[b][o][m] = sum_i wts[o][i] * u[b][i][m],   m < M  (M = ntau * nphi, or ntau for u0). */
+int pd_interp_mu(int B, int n2, long M, int nmu, const double* wts, const double* u, double* out, void* stream);
+
 /* FP64 FMA throughput probe (one launch of dependent-free DFMA chains); used
  * by bench.py to measure the FP64 roofline denominator on the box.
  * Returns the number of FLOPs the launch performs; time it with CUDA events. */

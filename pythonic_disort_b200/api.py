@@ -165,6 +165,19 @@ class _Solution:
             raise RuntimeError(f"libpydisort_b200: {what} failed with code {rc}")
 
     # -- launches ----------------------------------------------------------------
+    def interp_mu(self, vals, mu):
+        """``vals`` [B, 2N, ...] on the device -> [B, nmu, ...] at the polar-angle cosines ``mu`` (row f1)."""
+        W = torch.as_tensor(barycentric_weight_matrix(mu, self.NQuad // 2), dtype=_F64, device=self.dev).contiguous()
+        nmu = W.shape[0]
+        vals = vals.contiguous()
+        M = int(np.prod(vals.shape[2:])) if vals.ndim > 2 else 1
+        out = torch.empty((self.B, nmu) + tuple(vals.shape[2:]), dtype=_F64, device=self.dev)
+        _mark("begin", self.dev)
+        self._check(self.lib.pd_interp_mu(self.B, self.NQuad, M, nmu, _ptr(W), _ptr(vals), _ptr(out), _stream(self.dev)),
+                    "pd_interp_mu")
+        _mark("interp_mu", self.dev)
+        return out, nmu
+
     def eval_flux(self, tau, anti):
         memo = getattr(self, "_flux_memo", None)  # flux_up(tau) then flux_down(tau): one launch serves both
         if memo is not None and memo[0] is tau and memo[1] == bool(anti) and memo[4] == _content_tag(tau):
@@ -214,6 +227,33 @@ class _Solution:
                                        _stream(self.dev)), "pd_eval_u")
         _mark("eval_u", self.dev)
         return u, ulast, ph, ntau, nphi
+
+
+def barycentric_weight_matrix(mu, N):
+    """Weight matrix [nmu, 2N] of ``subroutines.interpolate`` (subroutines.py:614-705): row o holds the barycentric
+    Lagrange weights of the N Gauss-Legendre streams of the hemisphere of ``mu[o]`` (``mu > 0``: the upward streams
+    ``mu_i``, columns 0..N-1; otherwise the downward streams ``-mu_i``, columns N..2N-1) and zeros elsewhere."""
+    from .subroutines import Gauss_Legendre_quad
+    mu = np.atleast_1d(np.asarray(mu, dtype=np.float64))
+    nodes = Gauss_Legendre_quad(N)[0]
+    diff = nodes[:, None] - nodes[None, :]
+    np.fill_diagonal(diff, 1.0)
+    bw = 1.0 / np.prod(diff, axis=1)  # w_j = 1 / prod_{k != j} (x_j - x_k); identical for the mirrored node set up to sign
+    W = np.zeros((mu.shape[0], 2 * N))
+    for o, x in enumerate(mu):
+        up = x > 0
+        xj = nodes if up else -nodes
+        wj = bw if up else bw * (-1.0) ** (N - 1)
+        d = x - xj
+        hit = np.nonzero(d == 0.0)[0]
+        if hit.size:
+            row = np.zeros(N)
+            row[hit[0]] = 1.0
+        else:
+            t = wj / d
+            row = t / np.sum(t)
+        W[o, (0 if up else N):(N if up else 2 * N)] = row
+    return W
 
 
 def _bc_tensor(b, name, B, N, NF, batched, T):
@@ -587,6 +627,19 @@ def _make_functions(sol):
             outs += (sol.tau_arr_in,)
         return outs[0] if len(outs) == 1 else outs
 
+    def u_at_mu(mu, tau, phi, is_antiderivative_wrt_tau=False):
+        """u interpolated to user polar angles on the device (used by ``subroutines.interpolate``)."""
+        val, _, _, ntau, nphi = sol.eval_u(tau, phi, is_antiderivative_wrt_tau, sol.nt, False)
+        out, nmu = sol.interp_mu(val, mu)
+        return sol._finish(out, (nmu, ntau, nphi))
+
+    def u0_at_mu(mu, tau, is_antiderivative_wrt_tau=False):
+        val, _, ntau = sol.eval_u0(tau, is_antiderivative_wrt_tau, False)
+        out, nmu = sol.interp_mu(val, mu)
+        return sol._finish(out, (nmu, ntau))
+
+    u.at_mu = u_at_mu
+    u0.at_mu = u0_at_mu
     for fn, kind in ((flux_up, "flux_up"), (flux_down, "flux_down"), (u0, "u0"), (u, "u")):
         fn.kind = kind
         fn.batched = sol.batched

@@ -233,8 +233,11 @@ static bool use_mma(int N) {
     return true;
 }
 
+#ifndef PD_MMA_MINB
+#define PD_MMA_MINB 4  // resident CTAs per SM the N = 8 tensor-core kernel is compiled for
+#endif
 template <int N>
-__global__ void __launch_bounds__(128, (N == 8) ? 4 : 2) k_stage_b_mma(PdStageB a, double* hist, long hist_doubles) {
+__global__ void __launch_bounds__(128, (N == 8) ? PD_MMA_MINB : 2) k_stage_b_mma(PdStageB a, double* hist, long hist_doubles) {
     extern __shared__ double smem[];
     const int SD = PdStageBMma<N>::smem_doubles(a.L);
     const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5;
@@ -270,7 +273,7 @@ static StageBPlan plan_mma(int B, int NF, int L) {
     if (blocks > (long)PD_NUM_SMS * ctas_per_sm) blocks = (long)PD_NUM_SMS * ctas_per_sm;
     p.blocks = (int)blocks;
     p.slots = blocks * p.wpb;
-    p.hist_doubles = (long)L * PdStageBMma<N>::HIST_PER_LAYER;
+    p.hist_doubles = PdStageBMma<N>::scratch_doubles(L);
     return p;
 }
 

@@ -90,7 +90,48 @@ __global__ void __launch_bounds__(256) k_nt(PdEval a, PdNT nt, const double* __r
     }
 }
 
+// u or u0 at user polar angles: contraction of the stream axis with the barycentric weight matrix
+// (subroutines.py:614-705).  One thread per (column, point); NO outputs per pass; u is read once per pass, coalesced.
+template <int NO>
+__global__ void k_interp_mu(int n2, long M, int nmu, const double* __restrict__ wts, const double* __restrict__ u,
+                            double* __restrict__ out) {
+    extern __shared__ double smem[];  // [NO][n2] weights of this pass
+    const long chunks = (M + blockDim.x - 1) / blockDim.x;
+    const int o0 = blockIdx.y * NO;
+    const long b = blockIdx.x / chunks;
+    for (int idx = threadIdx.x; idx < NO * n2; idx += blockDim.x) {
+        const int o = o0 + idx / n2;
+        smem[idx] = (o < nmu) ? wts[(long)o * n2 + idx % n2] : 0.0;
+    }
+    __syncthreads();
+    const long mm = (blockIdx.x % chunks) * blockDim.x + threadIdx.x;
+    if (mm >= M) return;
+    double acc[NO];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) acc[o] = 0.0;
+    const double* ub = u + b * n2 * M + mm;
+    for (int i = 0; i < n2; ++i) {
+        const double v = ub[(long)i * M];
+#pragma unroll
+        for (int o = 0; o < NO; ++o) acc[o] = fma(smem[o * n2 + i], v, acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < NO; ++o)
+        if (o0 + o < nmu) out[(b * nmu + o0 + o) * M + mm] = acc[o];
+}
+
 extern "C" {
+
+int pd_interp_mu(int B, int n2, long M, int nmu, const double* wts, const double* u, double* out, void* stream) {
+    if (B < 1 || n2 < 2 || (n2 & 1) || M < 1 || nmu < 1 || !wts || !u || !out) return -40;
+    constexpr int NO = 8;
+    const int threads = 256;
+    const long blocks = (long)B * ((M + threads - 1) / threads);
+    if (blocks > 2147483647L || (nmu + NO - 1) / NO > 65535) return -41;
+    const dim3 grid((unsigned)blocks, (unsigned)((nmu + NO - 1) / NO));
+    k_interp_mu<NO><<<grid, threads, (size_t)NO * n2 * 8, pd_stream(stream)>>>(n2, M, nmu, wts, u, out);
+    return (int)cudaGetLastError();
+}
 
 static PdEval make_eval(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau, int anti) {
     PdEval a;

@@ -9,17 +9,18 @@
 //
 // One warp owns one (column, mode) system.  The 3N x 4N panel of stage l (N carried rows + 2N rows of interface l;
 // _solve_for_coeffs.py:139-323 as in pd_stage_b.cuh) lives in registers as RT x CT accumulator tiles of
-// mma.m8n8k4 (tile row = lane / 4, tile columns = 2 (lane % 4) + {0, 1}) and is mirrored in shared memory, from
-// where the other layouts are picked up.  Per block of four columns J = j0 .. j0 + 3:
-//   1. the live tiles are stored to the mirror; every lane picks up the four J-values of "its" row (one lane per
-//      row; the right-hand side lives in this layout and is eliminated like a fifth column);
+// mma.m8n8k4 (tile row = lane / 4, tile columns = 2 (lane % 4) + {0, 1}).  Per block of four columns J = j0 .. j0 + 3:
+//   1. the lanes that hold columns J publish them to shared memory; every lane picks up the four J-values of "its"
+//      row (one lane per row; the right-hand side lives in this layout and is eliminated like a fifth column);
 //   2. the four pivots are found one after the other with partial pivoting over the rows still in play (32-bit
 //      magnitude key + REDUX.MAX; the pivot lane's block values, multipliers, right-hand side and -1/pivot are
 //      broadcast with shuffles -- shorter than a shared-memory round trip, and this chain is what bounds the kernel).  The elimination is Gauss-Jordan without normalisation (earlier pivot
 //      rows keep being reduced) and is applied to the four block columns only; every row accumulates its multipliers
 //      g with respect to the ORIGINAL four pivot rows:   new_row_i = row_i + sum_k g[i][k] * row_{p_k};
-//   3. A = g (3N x 4, through shared memory) and B = the four pivot rows (4 x 4N, from the mirror) are loaded in
-//      operand layout and every live tile gets one DMMA:  C = A B + C.
+//   3. A = g (3N x 4) and B = the four pivot rows as they were at the start of the block (4 x 4N, published by the
+//      quads that hold them) go through shared memory into operand layout and every live tile gets one DMMA:
+//      C = A B + C.  (The kernel is bound by the shared-memory / shuffle pipe, profiles/: only the block columns,
+//      the multipliers and the four pivot rows travel through it, not the panel.)
 // After the 2N/4 blocks the pivot row of column j holds pivot_j times row j of U11^-1 [U12 | y]; M_l = -U12 and z_l
 // go to the history buffer, the N rows that were never pivots are the next stage's carry (their columns shift by
 // 2N: a move of whole tiles), and the freed rows load interface l + 1.  Back substitution x_l = z_l + M_l x_{l+1}.
@@ -44,12 +45,15 @@ struct PdStageBMma {
     static constexpr int N2 = 2 * N, NR = 3 * N, RC = 4 * N, RT = NR / 8, CT = RC / 8, HT = CT / 2, NB = N2 / 4;
     static constexpr int RPL = (NR + 31) / 32;  // rows per lane in the one-lane-per-row layout
     static constexpr int NT8 = N / 8;           // tiles per N columns
-    static constexpr int RS = RC + 8;           // row stride of the mirror: 8 (mod 16) doubles, so that the 128-bit tile
-                                                // stores of a quarter warp (two rows) fall into disjoint bank halves
-    static constexpr int MIRROR = NR * RS, BLK = NR * 4, PKT = 2 * 8;
-    static constexpr int SMEM_FIXED = MIRROR + BLK + PKT + N * N + N2 + NR + NR / 2;
-    PD_HD static int smem_doubles(int L) { return (SMEM_FIXED + L * N + L + 1 + 1) & ~1; }
+    static constexpr int PS = RC + 4;           // stride of a published pivot row: 4 (mod 16) doubles, so that the
+                                                // operand loads of a half warp touch 16 distinct bank pairs
+    static constexpr int BLK = NR * 4, PROW = 4 * PS, PKT = 2 * 8;
+    static constexpr int SMEM_FIXED = 2 * BLK + PROW + PKT + N * N + N2 + NR + NR / 2;
+    PD_HD static int smem_doubles(int L) { return (SMEM_FIXED + L + 1 + 1) & ~1; }
     static constexpr long HIST_PER_LAYER = (long)N2 * N2 + N2;  // M_l [2N][2N] row-major, z_l [2N]
+    // per-slot scratch in global memory: the history of all layers, then exp(-k_l dtau*_l) [L][N] (kept out of shared
+    // memory: the footprint per warp decides how many systems an SM keeps in flight)
+    PD_HD static long scratch_doubles(int L) { return (long)L * HIST_PER_LAYER + (long)L * N; }
     using mask_t = typename std::conditional<(NR > 32), unsigned long long, unsigned>::type;
 };
 
@@ -76,19 +80,20 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
     using F = PdStageBMma<N>;
     using mask_t = typename F::mask_t;
     constexpr int N2 = F::N2, NR = F::NR, RT = F::RT, CT = F::CT, HT = F::HT, NB = F::NB, RPL = F::RPL;
-    constexpr int NT8 = F::NT8, RS = F::RS;
+    constexpr int NT8 = F::NT8, PS = F::PS;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, q = lane >> 2, t = lane & 3;
     const int L = A.L;
-    double* mir = sm;                    // [NR][RS] mirror of the panel
-    double* blkA = mir + F::MIRROR;      // [NR][4] A operand: the multipliers g
-    double* pkt = blkA + F::BLK;         // [2][8] pivot packet, double buffered
+    double* blkV = sm;                   // [NR][4] the block's four columns, one row per slot
+    double* blkA = blkV + F::BLK;        // [NR][4] A operand: the multipliers g
+    double* prow = blkA + F::BLK;        // [4][PS] B operand: the block's four pivot rows as they were at its start
+    double* pkt = prow + F::PROW;        // [2][8] pivot packet, double buffered
     double* R = pkt + F::PKT;            // [N][N]
     double* xs = R + N * N;              // [2N]
     double* npOf = xs + N2;              // [NR] -1/pivot of a row slot that was a pivot row in this stage
     int* colOf = reinterpret_cast<int*>(npOf + NR);  // [NR] its pivot column, -1: none
-    double* Eall = npOf + NR + NR / 2;   // [L][N]  exp(-k_l dtau*_l)
-    double* att = Eall + (long)L * N;    // [L+1]   exp(-tau*_l / mu0)
+    double* att = npOf + NR + NR / 2;    // [L+1]   exp(-tau*_l / mu0)
+    double* Eall = hist + (long)L * F::HIST_PER_LAYER;  // [L][N]  exp(-k_l dtau*_l), global scratch of this slot
 
     const long sys = (long)b * A.NF + m;
     const double* taus = A.taus + (long)b * (L + 1);
@@ -198,14 +203,16 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
                         const int nb = ct / NT8, cc0 = (ct % NT8) * 8 + 2 * t;
                         pd_d2 v = *reinterpret_cast<const pd_d2*>(Grow(l + (nb >> 1), idx, nb & 1) + cc0);
                         if (nb == 0) {
-                            v.x *= E[cc0];
-                            v.y *= E[cc0 + 1];
+                            const pd_d2 e = *reinterpret_cast<const pd_d2*>(E + cc0);
+                            v.x *= e.x;
+                            v.y *= e.y;
                         } else if (nb == 2) {
                             v.x = -v.x;
                             v.y = -v.y;
                         } else if (nb == 3) {
-                            v.x *= -E[N + cc0];
-                            v.y *= -E[N + cc0 + 1];
+                            const pd_d2 e = *reinterpret_cast<const pd_d2*>(E + N + cc0);
+                            v.x *= -e.x;
+                            v.y *= -e.y;
                         }
                         c[rt][ct][0] = v.x;
                         c[rt][ct][1] = v.y;
@@ -278,17 +285,17 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
         // ---- elimination of the 2N columns of C_l in blocks of four ----
         pd_static_for<0, NB>([&](auto KB) {
             constexpr int kb = decltype(KB)::value;
-            constexpr int j0 = 4 * kb, ctlive = j0 / 8, ctmin = (j0 + 4) / 8;
-            // 1. live tiles to the mirror; one row per lane picks up the block's columns
+            constexpr int j0 = 4 * kb, ctJ = j0 / 8, t0 = (j0 % 8) / 2, ctmin = (j0 + 4) / 8;
+            // 1. the lanes that hold the block's columns publish them; one row per lane picks them up
+            if ((t >> 1) == (t0 >> 1)) {
 #pragma unroll
-            for (int rt = 0; rt < RT; ++rt)
-#pragma unroll
-                for (int ct = ctlive; ct < CT; ++ct) {
+                for (int rt = 0; rt < RT; ++rt) {
                     pd_d2 v2;
-                    v2.x = c[rt][ct][0];
-                    v2.y = c[rt][ct][1];
-                    *reinterpret_cast<pd_d2*>(mir + (rt * 8 + q) * RS + ct * 8 + 2 * t) = v2;
+                    v2.x = c[rt][ctJ][0];
+                    v2.y = c[rt][ctJ][1];
+                    *reinterpret_cast<pd_d2*>(blkV + (rt * 8 + q) * 4 + 2 * (t - t0)) = v2;
                 }
+            }
             __syncwarp();
             double v[RPL][4], g[RPL][4];
 #pragma unroll
@@ -297,8 +304,8 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
                 pd_d2 lo, hi;
                 lo.x = lo.y = hi.x = hi.y = 0.0;
                 if (slot < NR) {
-                    lo = *reinterpret_cast<const pd_d2*>(mir + slot * RS + j0);
-                    hi = *reinterpret_cast<const pd_d2*>(mir + slot * RS + j0 + 2);
+                    lo = *reinterpret_cast<const pd_d2*>(blkV + slot * 4);
+                    hi = *reinterpret_cast<const pd_d2*>(blkV + slot * 4 + 2);
                 }
                 v[r][0] = lo.x; v[r][1] = lo.y; v[r][2] = hi.x; v[r][3] = hi.y;
             }
@@ -383,15 +390,28 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
                     *reinterpret_cast<pd_d2*>(blkA + slot * 4 + 2) = hi;
                 }
             }
+            // the quads that hold this block's pivot rows publish them (values as of the start of the block)
+#pragma unroll
+            for (int rt = 0; rt < RT; ++rt) {
+                const int slot = rt * 8 + q;
+                const int kidx = (slot == p[0]) ? 0 : (slot == p[1]) ? 1 : (slot == p[2]) ? 2 : (slot == p[3]) ? 3 : -1;
+                if (kidx >= 0) {
+                    double* dst = prow + kidx * PS + 2 * t;
+#pragma unroll
+                    for (int ct = ctmin; ct < CT; ++ct) {
+                        pd_d2 v2;
+                        v2.x = c[rt][ct][0];
+                        v2.y = c[rt][ct][1];
+                        *reinterpret_cast<pd_d2*>(dst + ct * 8) = v2;
+                    }
+                }
+            }
             __syncwarp();
-            const int pt = (t & 2) ? ((t & 1) ? p[3] : p[2]) : ((t & 1) ? p[1] : p[0]);
-            const double* brow = mir + pt * RS + q;
             double af[RT], bf[CT];
 #pragma unroll
             for (int rt = 0; rt < RT; ++rt) af[rt] = blkA[(rt * 8 + q) * 4 + t];
 #pragma unroll
-            for (int ct = ctmin; ct < CT; ++ct) bf[ct] = brow[ct * 8];
-            __syncwarp();  // the mirror is rewritten at the start of the next block
+            for (int ct = ctmin; ct < CT; ++ct) bf[ct] = prow[t * PS + ct * 8 + q];
 #pragma unroll
             for (int rt = 0; rt < RT; ++rt)
 #pragma unroll

@@ -243,7 +243,13 @@ def affine_transform_poly_coeffs(poly_coeffs, a_arr, b_arr):
 def interpolate(u):
     """Barycentric interpolation in ``mu`` of ``u`` or ``u0`` (each hemisphere
     separately), giving ``u(mu, tau, phi)`` / ``u0(mu, tau)``
-    (subroutines.py:614-705).  Host-side post-processing."""
+    (subroutines.py:614-705).
+
+    For the output functions of ``pythonic_disort_b200.pydisort`` the
+    interpolation runs on the GPU (``pd_interp_mu``: the stream axis is
+    contracted with the barycentric weight matrix right after the evaluation
+    kernel, so only the ``[nmu, ntau, nphi]`` result leaves the device).  Any
+    other callable with the reference's signature is interpolated on the host."""
     kind = getattr(u, "kind", None)
     if kind is None:
         kind = {5: "u", 4: "u0"}.get(u.__code__.co_argcount)
@@ -251,16 +257,22 @@ def interpolate(u):
         raise ValueError("This subroutine can only interpolate u or u0.")
     batched = getattr(u, "batched", False)
     ax = 1 if batched else 0
-    probe = _to_numpy(u(0, 0) if kind == "u" else u(0))
-    N = probe.shape[ax] // 2
-    mu_pos = Gauss_Legendre_quad(N)[0]
-    up = scipy.interpolate.BarycentricInterpolator(mu_pos)
-    dn = scipy.interpolate.BarycentricInterpolator(-mu_pos)
+    at_mu = getattr(u, "at_mu", None)
 
-    def _interp(mu, values):
+    def _check_mu(mu):
         if not np.all(np.abs(mu) <= 1):
             raise ValueError("mu values must be between -1 and 1.")
-        mu = np.atleast_1d(mu)
+        return np.atleast_1d(mu)
+
+    if at_mu is None:  # host path for foreign callables
+        probe = _to_numpy(u(0, 0) if kind == "u" else u(0))
+        N = probe.shape[ax] // 2
+        mu_pos = Gauss_Legendre_quad(N)[0]
+        up = scipy.interpolate.BarycentricInterpolator(mu_pos)
+        dn = scipy.interpolate.BarycentricInterpolator(-mu_pos)
+
+    def _interp(mu, values):
+        mu = _check_mu(mu)
         vals = np.moveaxis(_to_numpy(values), ax, 0)
         out = np.empty((len(mu),) + vals.shape[1:])
         pos = mu > 0
@@ -275,16 +287,27 @@ def interpolate(u):
     if kind == "u":
         def u_interpol(mu, tau, phi, is_antiderivative_wrt_tau=False, return_Fourier_error=False,
                        return_tau_arr=False):
-            res = u(tau, phi, is_antiderivative_wrt_tau, return_Fourier_error, return_tau_arr)
+            if at_mu is not None:
+                val = at_mu(_check_mu(mu), tau, phi, is_antiderivative_wrt_tau)
+                if return_Fourier_error or return_tau_arr:
+                    res = u(tau, phi, is_antiderivative_wrt_tau, return_Fourier_error, return_tau_arr)
+                    return (val,) + tuple(res[1:])
+                return val
             if return_Fourier_error or return_tau_arr:
+                res = u(tau, phi, is_antiderivative_wrt_tau, return_Fourier_error, return_tau_arr)
                 return (_interp(mu, res[0]),) + tuple(res[1:])
-            return _interp(mu, res)
+            return _interp(mu, u(tau, phi, is_antiderivative_wrt_tau))
     else:
         def u_interpol(mu, tau, is_antiderivative_wrt_tau=False, return_tau_arr=False):
-            res = u(tau, is_antiderivative_wrt_tau, return_tau_arr)
+            if at_mu is not None:
+                val = at_mu(_check_mu(mu), tau, is_antiderivative_wrt_tau)
+                if return_tau_arr:
+                    return (val,) + tuple(u(tau, is_antiderivative_wrt_tau, True)[1:])
+                return val
             if return_tau_arr:
+                res = u(tau, is_antiderivative_wrt_tau, return_tau_arr)
                 return (_interp(mu, res[0]),) + tuple(res[1:])
-            return _interp(mu, res)
+            return _interp(mu, u(tau, is_antiderivative_wrt_tau))
     return u_interpol
 
 

@@ -160,10 +160,12 @@ def column_call(ens, b):
     return args, kwargs
 
 
-def run_reference_like(pydisort_fn, ens, columns=None):
+def run_reference_like(pydisort_fn, ens, columns=None, at_user_mu=False):
     """Evaluate a one-column-per-call implementation with the reference's
     signature (the reference itself, or the oracle) on the ensemble's level
-    grid.  Returns arrays stacked over columns."""
+    grid.  Returns arrays stacked over columns.  ``at_user_mu``: ensembles that
+    name user polar angles (``mu_user``) get ``u`` there through the host-side
+    ``interpolate`` (what a user of the reference would call)."""
     cols = range(ens["B"]) if columns is None else columns
     want_u = "u" in ens["outputs"]
     Fp, Fmd, Fdir, U0, Uu = [], [], [], [], []
@@ -176,7 +178,9 @@ def run_reference_like(pydisort_fn, ens, columns=None):
         Fmd.append(dn[0])
         Fdir.append(np.broadcast_to(dn[1], np.shape(dn[0])))
         U0.append(out[3](t))
-        if want_u:
+        if want_u and at_user_mu and ens.get("mu_user") is not None:
+            Uu.append(sub.interpolate(out[4])(ens["mu_user"], t, ens["phi_eval"]))
+        elif want_u:
             Uu.append(out[4](t, ens["phi_eval"]))
     res = dict(flux_up=np.array(Fp), flux_down_diffuse=np.array(Fmd), flux_down_direct=np.array(Fdir),
                u0=np.array(U0))

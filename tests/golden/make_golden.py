@@ -14,6 +14,8 @@ What it does
      quadrature nodes (that is all the solver ever asks of them);
   2. copies the Stamnes DISORT 4.0.99 result files the tests compare against
      (data, not code) to ``tests/golden/stamnes/``;
+  4. (``interpolate``) runs the reference's ``subroutines.interpolate`` on its own ``u`` / ``u0`` at the user
+     polar angles of config 5 -> ``tests/golden/interpolate.npz``;
   3. runs the reference on fixed subsets of the three synthetic ensembles of
      SURVEY.md section 8(d) (generator: pythonic_disort_b200/synthetic.py) and
      stores inputs-by-seed + outputs in ``tests/golden/ensemble_<name>.npz``.
@@ -216,11 +218,39 @@ def run_ensembles():
         print(f"ensemble {name}: {ncol} columns")
 
 
+MU_USER = np.array([0.1, 0.5, 0.9, -0.1, -0.5, -0.9])  # user polar angles
+
+
+def run_interpolate():
+    """Row f1: the reference's ``subroutines.interpolate`` (subroutines.py:614-705) on its own ``u`` / ``u0`` for
+    columns of the HA ensemble (config 5) and of the SW ensemble (NT-corrected intensities)."""
+    from pythonic_disort_b200 import synthetic
+    out = {"mu_user": MU_USER}
+    for name, ncol in (("ha", 2), ("sw", 3)):
+        ens = synthetic.make(name, ncol)
+        um, u0m = [], []
+        for b in range(ncol):
+            args, kwargs = synthetic.column_call(ens, b)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                res = _orig_pydisort(*args, **kwargs)
+            t = ens["tau_eval"][b]
+            um.append(ref_sub.interpolate(res[4])(MU_USER, t, ens["phi_eval"]))
+            u0m.append(ref_sub.interpolate(res[3])(MU_USER, t))
+        out[f"{name}_ncol"] = np.array(ncol)
+        out[f"{name}_u"] = np.array(um)
+        out[f"{name}_u0"] = np.array(u0m)
+        print(f"interpolate {name}: {ncol} columns", out[f"{name}_u"].shape)
+    np.savez_compressed(os.path.join(HERE, "interpolate.npz"), **out)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["suite", "stamnes", "ensembles"]
+    what = sys.argv[1:] or ["suite", "stamnes", "ensembles", "interpolate"]
     if "suite" in what:
         run_reference_suite()
     if "stamnes" in what:
         copy_stamnes()
     if "ensembles" in what:
         run_ensembles()
+    if "interpolate" in what:
+        run_interpolate()

@@ -187,6 +187,18 @@ int pd_eval_u(const pd_config* cfg, const pd_state* st, const double* tau_q, int
     return 0;
 }
 
+int pd_interp_mu(int B, int n2, long M, int nmu, const double* wts, const double* u, double* out, void*) {
+    if (B < 1 || n2 < 2 || (n2 & 1) || M < 1 || nmu < 1 || !wts || !u || !out) return -40;
+    for (long b = 0; b < B; ++b)
+        for (int o = 0; o < nmu; ++o)
+            for (long m = 0; m < M; ++m) {
+                double acc = 0.0;
+                for (int i = 0; i < n2; ++i) acc = fma(wts[(long)o * n2 + i], u[(b * n2 + i) * M + m], acc);
+                out[(b * nmu + o) * M + m] = acc;
+            }
+    return 0;
+}
+
 double pd_fp64_probe(double*, int, void*) { return -1.0; }
 
 }  // extern "C"

@@ -89,3 +89,31 @@ def check_ensemble_vs_golden(pydisort, name, tol=1e-9):
     ens = synthetic.make(name, ncol)
     got = run_batched(pydisort, ens)
     return compare_fields(got, {k: gold[k] for k in got}, ncol, tol, name)
+
+
+def check_interpolate_vs_golden(pd_module, name, tol=1e-9):
+    """Row f1: ``subroutines.interpolate`` on the batched output functions (GPU: ``pd_interp_mu``) against the
+    reference's own ``interpolate`` (tests/golden/interpolate.npz, made by make_golden.py), and against the
+    host (SciPy) interpolation of the same closures."""
+    gold = np.load(os.path.join(golden_io.GOLDEN, "interpolate.npz"))
+    ncol, mu = int(gold[f"{name}_ncol"]), gold["mu_user"]
+    ens = synthetic.make(name, ncol)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = pd_module.pydisort(*ens["args"], **ens["kwargs"])
+    t, phi = ens["tau_eval"], ens["phi_eval"]
+    got_u = to_np(pd_module.subroutines.interpolate(out[4])(mu, t, phi))
+    got_u0 = to_np(pd_module.subroutines.interpolate(out[3])(mu, t))
+    assert got_u.shape == gold[f"{name}_u"].shape and got_u0.shape == gold[f"{name}_u0"].shape
+    worst = 0.0
+    for b in range(ncol):
+        for g, r in ((got_u[b], gold[f"{name}_u"][b]), (got_u0[b], gold[f"{name}_u0"][b])):
+            err, _, _ = golden_io.parity(g, r)
+            assert err <= tol, (name, b, err)
+            worst = max(worst, err)
+    # the same closures through the host path (a foreign callable has no `at_mu`)
+    plain = lambda tau, phi_, a=False, f=False, r=False: out[4](tau, phi_, a, f, r)  # noqa: E731
+    plain.kind, plain.batched = "u", True
+    host = pd_module.subroutines.interpolate(plain)(mu, t, phi)
+    np.testing.assert_allclose(got_u, host, rtol=1e-10, atol=1e-12 * np.max(np.abs(host)))
+    return worst

@@ -44,6 +44,12 @@ def test_ensembles_vs_reference_golden(name):
     parity_suite.check_ensemble_vs_golden(pd.pydisort, name)
 
 
+@pytest.mark.parametrize("name", ["ha", "sw"])
+def test_interpolate_at_user_polar_angles_on_the_device(name):
+    """Row f1 (subroutines.py:614-705): pd_interp_mu against the reference's own interpolate()."""
+    parity_suite.check_interpolate_vs_golden(pd, name)
+
+
 @pytest.mark.parametrize("name,ncol,first", [("sw", 48, 1000), ("lw", 256, 5000), ("tp1", 6, 0), ("tp9c", 2, 0)])
 def test_ensembles_vs_live_oracle(name, ncol, first):
     from oracle import disort_oracle

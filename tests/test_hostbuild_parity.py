@@ -35,6 +35,11 @@ def test_ensembles(name):
     parity_suite.check_ensemble_vs_golden(pd.pydisort, name)
 
 
+@pytest.mark.parametrize("name", ["ha", "sw"])
+def test_interpolate_at_user_polar_angles(name):
+    parity_suite.check_interpolate_vs_golden(pd, name)
+
+
 def _counts(lib):
     import ctypes
     lib.pd_hostsim_count.restype = ctypes.c_long

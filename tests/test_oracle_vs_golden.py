@@ -65,3 +65,22 @@ def test_oracle_corrections_improve_on_stamnes():
     assert np.mean(plain[0] - corrected[0]) > 0
     assert np.mean(plain[2] - corrected[2]) > 0
     assert np.mean(plain[6] - corrected[6]) > 0
+
+
+def test_oracle_with_interpolate_reproduces_the_reference_at_user_polar_angles():
+    """Row f1: the oracle's u through the host-side interpolate() against the reference's interpolate() output
+    (tests/golden/interpolate.npz) -- pins the CPU arm of the HA bench, which evaluates at user polar angles."""
+    import os
+    import warnings
+
+    import golden_io
+    from oracle import disort_oracle
+    from pythonic_disort_b200 import synthetic
+    gold = np.load(os.path.join(golden_io.GOLDEN, "interpolate.npz"))
+    ens = synthetic.make("ha", 1)
+    ens["mu_user"] = gold["mu_user"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = synthetic.run_reference_like(disort_oracle.pydisort, ens, at_user_mu=True)["u"][0]
+    err, _, _ = golden_io.parity(got, gold["ha_u"][0])
+    assert err <= 1e-9, err
