@@ -48,7 +48,7 @@ struct PdStageBMma {
     static constexpr int PS = RC + 4;           // stride of a published pivot row: 4 (mod 16) doubles, so that the
                                                 // operand loads of a half warp touch 16 distinct bank pairs
     static constexpr int BLK = NR * 4, PROW = 4 * PS, PKT = 2 * 8;
-    static constexpr int SMEM_FIXED = 2 * BLK + PROW + PKT + N * N + N2 + NR + NR / 2;
+    static constexpr int SMEM_FIXED = 2 * BLK + PROW + PKT + N * N + N2 + NR + NR / 2 + NR / 2;
     PD_HD static int smem_doubles(int L) { return (SMEM_FIXED + L + 1 + 1) & ~1; }
     static constexpr long HIST_PER_LAYER = (long)N2 * N2 + N2;  // M_l [2N][2N] row-major, z_l [2N]
     // per-slot scratch in global memory: the history of all layers, then exp(-k_l dtau*_l) [L][N] (kept out of shared
@@ -92,7 +92,8 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
     double* xs = R + N * N;              // [2N]
     double* npOf = xs + N2;              // [NR] -1/pivot of a row slot that was a pivot row in this stage
     int* colOf = reinterpret_cast<int*>(npOf + NR);  // [NR] its pivot column, -1: none
-    double* att = npOf + NR + NR / 2;    // [L+1]   exp(-tau*_l / mu0)
+    int* kOf = colOf + NR;               // [NR] index (0..3) of a row slot among the current block's pivots, -1: none
+    double* att = npOf + NR + NR / 2 + NR / 2;  // [L+1]   exp(-tau*_l / mu0)
     double* Eall = hist + (long)L * F::HIST_PER_LAYER;  // [L][N]  exp(-k_l dtau*_l), global scratch of this slot
 
     const long sys = (long)b * A.NF + m;
@@ -310,7 +311,9 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
                 v[r][0] = lo.x; v[r][1] = lo.y; v[r][2] = hi.x; v[r][3] = hi.y;
             }
             // 2. four pivots, partial pivoting over the rows in play; g: new_row = row + sum_k g[k] * (original pivot row k)
-            int p[4];
+            int p[4], myk[RPL];
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) myk[r] = -1;
             pd_static_for<0, 4>([&](auto KI) {
                 constexpr int k = decltype(KI)::value;
                 unsigned key[RPL], kbest = 0u;
@@ -375,6 +378,7 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
                     if (mine) {
                         act[r] = false;
                         pj[r] = j0 + k;
+                        myk[r] = k;
                         mynp[r] = npinv;
                     }
                 }
@@ -388,13 +392,15 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
                     lo.x = g[r][0]; lo.y = g[r][1]; hi.x = g[r][2]; hi.y = g[r][3];
                     *reinterpret_cast<pd_d2*>(blkA + slot * 4) = lo;
                     *reinterpret_cast<pd_d2*>(blkA + slot * 4 + 2) = hi;
+                    kOf[slot] = myk[r];
                 }
             }
-            // the quads that hold this block's pivot rows publish them (values as of the start of the block)
+            // the quads that hold this block's pivot rows publish them (values as of the start of the block); which
+            // slots those are travels through a small table written by the lanes that own the rows
+            __syncwarp();
 #pragma unroll
             for (int rt = 0; rt < RT; ++rt) {
-                const int slot = rt * 8 + q;
-                const int kidx = (slot == p[0]) ? 0 : (slot == p[1]) ? 1 : (slot == p[2]) ? 2 : (slot == p[3]) ? 3 : -1;
+                const int kidx = kOf[rt * 8 + q];
                 if (kidx >= 0) {
                     double* dst = prow + kidx * PS + 2 * t;
 #pragma unroll
