@@ -1,4 +1,6 @@
 // pd_kernel_eval.cu -- evaluation kernels (flux, u0, u, NT corrections) and their C entry points
+#include <stdlib.h>
+
 #include "pd_launch.h"
 
 // ============================================================================
@@ -87,6 +89,138 @@ __global__ void __launch_bounds__(256) k_nt(PdEval a, PdNT nt, const double* __r
         const double v = pd_nt_value(a, nt, b, i, l, tq, ts, phi_q[p], Rpos, Rneg, imsc, imsv,
                                      nt.leg_all + ((long)b * L + l) * NA, rinv);
         u[(((long)b * n2 + i) * a.ntau + t) * nphi + p] += resc * v;
+    }
+}
+
+// Nakajima-Tanaka corrections, tabulated form (production path for NLeg_all <= NA): one CTA per column.
+//   phase 1: TMS layer scans (warp 0), IMS constants (warp 1), per-layer series coefficients
+//            c_l[k] = omega*_l [ (2k+1) g_l[k] / (1 - f_l) - w*_l[k] ]   (p_true / (1-f) - p_trunc as ONE series), level -> layer;
+//   phase 2: everything that depends on (level, stream) only -- the exponentials of pd_nt_value -- once instead of per azimuth;
+//   phase 3: a thread owns one (stream, azimuth) pair, keeps P_k(nu) in registers and walks over levels: one dot product with
+//            broadcast 128-bit loads of c_l per output instead of two three-term recurrences.
+// Same formulas as pd_nt_value (pydisort.py:409-694), which stays the reference implementation for the host build and the
+// fallback for longer phase functions.
+template <int NA>
+__global__ void __launch_bounds__(256) k_nt_tab(PdEval a, PdNT nt, const double* __restrict__ phi_q, int nphi, double* u) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x;
+    const int n = a.N, n2 = 2 * n, L = a.L, NAr = a.NLeg_all, ntau = a.ntau;
+    if (a.st.colp[(long)b * PD_NCOLP + PD_COL_NT] == 0.0) return;  // gate of pydisort.py:375, column part
+    double* Rpos = smem;                     // [n][L]
+    double* Rneg = Rpos + n * L;             // [n][L]
+    double* imsc = Rneg + n * L;             // [NA]
+    double* imsv = imsc + NA;                // [2]
+    double* rinv = imsv + 2;                 // [NA + 2] 1/l
+    double* coef = rinv + NA + 2;            // [L][NA]
+    double* own = coef + (long)L * NA;       // [ntau][n2]
+    double* oth = own + (long)ntau * n2;     // [ntau][n2]
+    double* chi = oth + (long)ntau * n2;     // [ntau][n]
+    double* tsl = chi + (long)ntau * n;      // [ntau] scaled optical depth of the level
+    int* lay = reinterpret_cast<int*>(tsl + ntau);  // [ntau] its layer
+    const double* cp = a.st.colp + (long)b * PD_NCOLP;
+    const double mu0 = cp[PD_COL_MU0], I0 = cp[PD_COL_I0];
+    const double* taus = a.st.taus + (long)b * (L + 1);
+
+    for (int i = threadIdx.x; i <= NA + 1; i += blockDim.x) rinv[i] = (i > 0) ? 1.0 / (double)i : 0.0;
+    for (int i = threadIdx.x; i < NA; i += blockDim.x) imsc[i] = 0.0;
+    const int warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (warp == 0) {
+        SubWarp<32> g;
+        if (L > 1) pd_tms_scans(g, a, b, Rpos, Rneg);
+    } else if (warp == 1) {
+        SubWarp<32> g;
+        pd_ims_setup(g, a, nt, b, imsc, imsv);
+    } else {
+        const int tid = threadIdx.x - 64, nth = blockDim.x - 64;
+        for (int idx = tid; idx < L * NA; idx += nth) {
+            const int l = idx / NA, k = idx - l * NA;
+            double v = 0.0;
+            if (k < NAr) {
+                const double gk = (k == 0) ? 1.0 : nt.leg_all[((long)b * L + l) * NAr + k];
+                v = (2 * k + 1) * gk / (1.0 - nt.f[(long)b * L + l]);
+                if (k < a.NLeg) v -= nt.wleg[((long)b * L + l) * a.NLeg + k];
+                v *= nt.omega_s[(long)b * L + l];
+            }
+            coef[idx] = v;
+        }
+        for (int t = tid; t < ntau; t += nth) {
+            const double tq = a.tau_q[(long)b * ntau + t];
+            const int l = pd_locate(a.st.tau + (long)b * L, L, tq);
+            lay[t] = l;
+            tsl[t] = pd_scaled_tau(a, b, l, tq);
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: (level, stream) factors ----
+    for (int idx = threadIdx.x; idx < ntau * n2; idx += blockDim.x) {
+        const int t = idx / n2, i = idx - t * n2;
+        const bool up = i < n;
+        const int ii = up ? i : i - n;
+        const double mua = a.st.mu_nodes[ii], mi = 1.0 / mua;
+        const int l = lay[t];
+        const double ts = tsl[t], tq = a.tau_q[(long)b * ntau + t];
+        const double sc = a.st.scale_tau[(long)b * L + l];
+        const double ttop = taus[l], tbot = taus[l + 1];
+        const double e0 = exp(-ts / mu0);
+        double o, f2;
+        if (up) {
+            const double ex = exp((ts - tbot) * mi - tbot / mu0);
+            o = a.anti ? e0 / (-sc / mu0) - ex / (sc * mi) : e0 - ex;
+            f2 = (L > 1) ? Rpos[ii * L + l] * exp(mi * (ts - tbot)) : 0.0;
+        } else {
+            const double ex = exp((ttop - ts) * mi - ttop / mu0);
+            o = a.anti ? e0 / (-sc / mu0) + ex / (sc * mi) : e0 - ex;
+            f2 = (L > 1) ? Rneg[ii * L + l] * exp(mi * (ttop - ts)) : 0.0;
+            const double mu0s = imsv[1];
+            const double x = mi - 1.0 / mu0s;
+            double ch;
+            if (a.anti)
+                ch = ((mu0s - x * mu0s * (mu0s + tq)) * exp(-tq / mu0s) - mua * exp(-tq * mi)) / (mua * mu0s * x * x);
+            else
+                ch = ((tq - 1.0 / x) * exp(-tq / mu0s) + exp(-tq * mi) / x) / (mua * mu0s * x);
+            chi[t * n + ii] = ch;
+        }
+        own[idx] = o + f2;
+    }
+    __syncthreads();
+    // ---- phase 3: (stream, azimuth) pairs walk over the levels ----
+    const int ncombo = n2 * nphi;
+    const int slices = blockDim.x / ncombo > 0 ? blockDim.x / ncombo : 1;
+    const double resc = cp[PD_COL_RESCALE];
+    for (int c0 = threadIdx.x; c0 < ncombo * slices; c0 += blockDim.x) {
+        const int combo = c0 % ncombo, slice = c0 / ncombo;
+        const int i = combo / nphi, p = combo - i * nphi;
+        const bool up = i < n;
+        const int ii = up ? i : i - n;
+        const double mua = a.st.mu_nodes[ii];
+        const double mus = up ? mua : -mua;
+        const double nu = pd_nt_nu(a, b, i, phi_q[p]);
+        double P[NA];  // Legendre polynomials P_k(nu), registers
+        P[0] = 1.0;
+        P[1] = nu;
+#pragma unroll
+        for (int k = 1; k + 1 < NA; ++k) P[k + 1] = (fma(2.0, (double)k, 1.0) * nu * P[k] - (double)k * P[k - 1]) * rinv[k + 1];
+        double ims = 0.0;
+        if (!up) {
+#pragma unroll
+            for (int k = 0; k < NA; ++k) ims = fma(imsc[k], P[k], ims);
+            ims *= imsv[0];
+        }
+        const double pref = (I0 / (4.0 * PD_PI)) * (mu0 / (mu0 + mus));
+        for (int t = slice; t < ntau; t += slices) {
+            const double* cl = coef + (long)lay[t] * NA;
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < NA; k += 2) {
+                const pd_d2 c2 = *reinterpret_cast<const pd_d2*>(cl + k);
+                d0 = fma(c2.x, P[k], d0);
+                d1 = fma(c2.y, P[k + 1], d1);
+            }
+            double val = pref * (d0 + d1) * own[t * n2 + i];
+            if (!up) val = fma(ims, chi[t * n + ii], val);
+            u[(((long)b * n2 + i) * ntau + t) * nphi + p] += resc * val;
+        }
     }
 }
 
@@ -196,6 +330,17 @@ int pd_eval_u(const pd_config* cfg, const pd_state* st, const double* tau_q, int
         if (!omega || !f || !leg_all || !omega_s || !wleg) return -32;
         PdNT p;
         p.omega = omega; p.f = f; p.leg_all = leg_all; p.omega_s = omega_s; p.wleg = wleg;
+        // tabulated kernel for NLeg_all <= 32 (registers hold P_k(nu)); recurrence kernel otherwise or on request
+        const char* env = getenv("PD_NT_RECURRENCE");
+        constexpr int NA = 32;
+        const size_t smt = (size_t)(2 * a.N * a.L + NA + 2 + NA + 2 + (size_t)a.L * NA + (size_t)ntau * (5 * a.N + 1) +
+                                    (ntau + 1) / 2 + 2) * 8;
+        if (a.NLeg_all <= NA && 2 * a.N * nphi <= 256 && smt <= PD_SMEM_MAX_CTA && !(env && env[0] == '1')) {
+            e = cudaFuncSetAttribute(k_nt_tab<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smt);
+            if (e != cudaSuccess) return (int)e;
+            k_nt_tab<NA><<<a.B, 256, smt, pd_stream(stream)>>>(a, p, phi_q, nphi, u);
+            return (int)cudaGetLastError();
+        }
         const size_t sm2 = (size_t)(2 * a.N * a.L + 2 * a.NLeg_all + 4) * 8;
         if (sm2 > PD_SMEM_MAX_CTA) return -33;
         e = cudaFuncSetAttribute(k_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);

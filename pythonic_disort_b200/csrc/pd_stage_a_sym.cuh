@@ -21,6 +21,9 @@
 #include "pd_stage_a.cuh"
 
 #define PD_JACOBI_MAX_SWEEPS 12
+#ifndef PD_JACOBI_GROUP
+#define PD_JACOBI_GROUP 2  // rotations of a round whose parameters are computed together (divides N/2)
+#endif
 
 template <int N>
 struct PdSym {
@@ -29,6 +32,12 @@ struct PdSym {
     PD_HD static constexpr int idx(int i, int j) {  // upper-packed index of (i, j), any order
         return (i <= j) ? (i * N - i * (i - 1) / 2 + (j - i)) : (j * N - j * (j - 1) / 2 + (i - j));
     }
+    // round-robin tournament (circle method): round r = 0 .. N-2, game g = 0 .. N/2-1; the N/2 pairs of a round are
+    // disjoint and the N-1 rounds cover every pair once.  rr_p < rr_q.
+    PD_HD static constexpr int rr_a(int r, int g) { return (g == 0) ? N - 1 : (r + g) % (N - 1); }
+    PD_HD static constexpr int rr_b(int r, int g) { return (g == 0) ? r : (r - g + (N - 1)) % (N - 1); }
+    PD_HD static constexpr int rr_p(int r, int g) { return rr_a(r, g) < rr_b(r, g) ? rr_a(r, g) : rr_b(r, g); }
+    PD_HD static constexpr int rr_q(int r, int g) { return rr_a(r, g) < rr_b(r, g) ? rr_b(r, g) : rr_a(r, g); }
 };
 
 // sm: per-thread parking area with stride `ps` between consecutive doubles of one thread
@@ -198,6 +207,7 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
     for (int i = 0; i < N; ++i)
 #pragma unroll
         for (int j = 0; j < N; ++j) W[i * N + j] = (i == j) ? 1.0 : 0.0;
+    constexpr int GRP = (PD_JACOBI_GROUP < N / 2) ? PD_JACOBI_GROUP : N / 2;
     bool converged = false;
     for (int sweep = 0; sweep < PD_JACOBI_MAX_SWEEPS; ++sweep) {
         double off = 0.0, diag = 0.0;
@@ -213,34 +223,54 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
 #else
         if (converged || !ok) break;
 #endif
+        // Round-robin ("tournament") ordering: the N/2 rotations of a round act on disjoint index pairs, so the
+        // parameters of GRP = min(PD_JACOBI_GROUP, N/2) of them are computed together from the same T -- their rsqrt / rcp chains
+        // (about 200 cycles each, far longer than the 14 row/column pair updates they feed) overlap instead of
+        // serialising -- and the rotations are then applied one after the other.
 #pragma unroll
-        for (int p = 0; p < N - 1; ++p)
+        for (int rnd = 0; rnd < N - 1; ++rnd)
 #pragma unroll
-            for (int q = p + 1; q < N; ++q) {
-                const double apq = T[P::idx(p, q)], app = T[P::idx(p, p)], aqq = T[P::idx(q, q)];
-                // rotation that annihilates T(p,q); identity if it is already negligible
-                // t = tan(rotation angle) = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq),
-                // written without the division by apq:  t = sgn(d) 2 apq / (|d| + sqrt(d^2 + 4 apq^2)).
-                // (an item that has converged is frozen, so its result does not depend on its warp neighbours)
-                const bool tiny = converged || (apq * apq <= 1e-36 * fabs(app * aqq));
-                const double d = aqq - app, a2 = 2.0 * apq;
-                const double h = fma(d, d, a2 * a2);
-                const double den = fabs(d) + h * pd_rsqrt(h > 0.0 ? h : 1.0);
-                const double tn = tiny ? 0.0 : ((d >= 0.0) ? a2 : -a2) * pd_rcp(den > 0.0 ? den : 1.0);
-                const double c = pd_rsqrt(fma(tn, tn, 1.0)), s = tn * c;
-                T[P::idx(p, p)] = fma(-tn, apq, app);
-                T[P::idx(q, q)] = fma(tn, apq, aqq);
-                T[P::idx(p, q)] = tiny ? apq : 0.0;
+            for (int g0 = 0; g0 < N / 2; g0 += GRP) {
+                double cc[GRP], ss[GRP], tt[GRP];
+                bool tny[GRP];
 #pragma unroll
-                for (int r = 0; r < N; ++r) {
-                    if (r != p && r != q) {
-                        const double trp = T[P::idx(r, p)], trq = T[P::idx(r, q)];
-                        T[P::idx(r, p)] = fma(c, trp, -s * trq);
-                        T[P::idx(r, q)] = fma(s, trp, c * trq);
+                for (int gi = 0; gi < GRP; ++gi) {
+                    const int p = P::rr_p(rnd, g0 + gi), q = P::rr_q(rnd, g0 + gi);
+                    const double apq = T[P::idx(p, q)], app = T[P::idx(p, p)], aqq = T[P::idx(q, q)];
+                    // rotation that annihilates T(p,q); identity if it is already negligible
+                    // t = tan(rotation angle) = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq),
+                    // written without the division by apq:  t = sgn(d) 2 apq / (|d| + sqrt(d^2 + 4 apq^2)).
+                    // (an item that has converged is frozen, so its result does not depend on its warp neighbours)
+                    const bool tiny = converged || (apq * apq <= 1e-36 * fabs(app * aqq));
+                    const double d = aqq - app, a2 = 2.0 * apq;
+                    const double h = fma(d, d, a2 * a2);
+                    const double den = fabs(d) + h * pd_rsqrt(h > 0.0 ? h : 1.0);
+                    const double tn = tiny ? 0.0 : ((d >= 0.0) ? a2 : -a2) * pd_rcp(den > 0.0 ? den : 1.0);
+                    const double c = pd_rsqrt(fma(tn, tn, 1.0));
+                    cc[gi] = c;
+                    ss[gi] = tn * c;
+                    tt[gi] = tn;
+                    tny[gi] = tiny;
+                }
+#pragma unroll
+                for (int gi = 0; gi < GRP; ++gi) {
+                    const int p = P::rr_p(rnd, g0 + gi), q = P::rr_q(rnd, g0 + gi);
+                    const double c = cc[gi], s = ss[gi], tn = tt[gi];
+                    const double apq = T[P::idx(p, q)], app = T[P::idx(p, p)], aqq = T[P::idx(q, q)];
+                    T[P::idx(p, p)] = fma(-tn, apq, app);
+                    T[P::idx(q, q)] = fma(tn, apq, aqq);
+                    T[P::idx(p, q)] = tny[gi] ? apq : 0.0;
+#pragma unroll
+                    for (int r = 0; r < N; ++r) {
+                        if (r != p && r != q) {
+                            const double trp = T[P::idx(r, p)], trq = T[P::idx(r, q)];
+                            T[P::idx(r, p)] = fma(c, trp, -s * trq);
+                            T[P::idx(r, q)] = fma(s, trp, c * trq);
+                        }
+                        const double wp = W[r * N + p], wq = W[r * N + q];
+                        W[r * N + p] = fma(c, wp, -s * wq);
+                        W[r * N + q] = fma(s, wp, c * wq);
                     }
-                    const double wp = W[r * N + p], wq = W[r * N + q];
-                    W[r * N + p] = fma(c, wp, -s * wq);
-                    W[r * N + q] = fma(s, wp, c * wq);
                 }
             }
     }

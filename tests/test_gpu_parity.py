@@ -92,6 +92,7 @@ def test_cuda_tensor_inputs_give_cuda_outputs():
     {"PD_STAGE_B_MMA": "0"},                                  # three-rows-per-lane register kernel instead of the tensor-core one
     {"PD_STAGE_B_MMA": "0", "PD_STAGE_B_ROW1": "1"},          # one-row-per-lane register kernel (shuffle broadcast)
     {"PD_STAGE_B_MMA": "0", "PD_STAGE_B_ROW1": "1", "PD_STAGE_B_SHFL": "0"},         # ... shared-memory broadcast
+    {"PD_NT_RECURRENCE": "1"},                                # NT corrections by per-output recurrences (any NLeg_all)
     {"PD_STAGE_B_SMEM": "1"},                                 # shared-memory panel kernel instead of register rows
     {"PD_STAGE_B_SMEM": "1", "PD_STAGE_B_LS": "16"},          # ... two systems per warp
     {"PD_STAGE_B_GENERIC": "1", "PD_STAGE_A_GENERAL": "1"},   # size-generic kernels (what any other NQuad uses)
