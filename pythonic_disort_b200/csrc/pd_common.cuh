@@ -64,6 +64,18 @@ struct alignas(16) pd_d2 {  // two doubles moved with one 128-bit access
     double x, y;
 };
 
+// four consecutive doubles, 32-byte aligned, in one 256-bit store (sm_100: STG.256)
+PD_HD void pd_store4(double* p, double a, double b, double c, double d) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#else
+    p[0] = a;
+    p[1] = b;
+    p[2] = c;
+    p[3] = d;
+#endif
+}
+
 // 1/sqrt(x), x > 0 finite: hardware seed (MUFU.RSQ64H) + two Newton steps (about 1 ulp)
 PD_HD double pd_rsqrt(double x) {
 #if defined(__CUDA_ARCH__)

@@ -8,13 +8,14 @@
 // and for omega* < 1 both are positive definite, so the eigenproblem of
 // (alpha-beta)(alpha+beta) = X' S (_solve_for_gen_and_part_sols.py:179-183) becomes a symmetric one:
 //     S = L L^T (Cholesky),  T = L^T X' L,  T W = W diag(k^2),  W orthogonal,
-//     eigenvectors V^ = L^-T W,   U^ = (alpha+beta)^ V^ / k = -L W / k,   (V^)^-1 = W^T L^T.
+//     eigenvectors V^ = L^-T W,   U^ = (alpha+beta)^ V^ / k = -L W / k = -L L^T V^ / k,   (V^)^-1 = W^T L^T = V^T L L^T.
 // T is diagonalised by cyclic Jacobi rotations: no data-dependent branches or indices, so 32 items
 // run in lock-step in one warp with all matrices in registers, and Jacobi delivers the small
 // eigenvalues (omega* -> 1) to high relative accuracy.  The particular solutions reuse the
 // decomposition instead of LU factorisations:
-//     beam    (:209-231): p^ = V^ diag(1/(1/mu0^2 - k^2)) W^T L^T r,  q^ = mu0 [(x1-x2) - L L^T p^]
-//     thermal (:201-205): G^-1 [1/mu; -1/mu] = [y; -y],  y = (U^)^-1 D/mu = -k * W^T L^-1 (D/mu)
+//     beam    (:209-231): p^ = V^ diag(1/(1/mu0^2 - k^2)) V^T L L^T r,  q^ = mu0 [(x1-x2) - L L^T p^]
+//     thermal (:201-205): G^-1 [1/mu; -1/mu] = [y; -y],  y = (U^)^-1 D/mu = -k * W^T L^-1 (D/mu) = -k * V^T (D/mu)
+// (after the rotations W is overwritten by V^ row by row while the G blocks are written, so only V^ and L are kept)
 // If S is not numerically positive definite or Jacobi does not converge, the item is flagged
 // (K[item][0] = NaN) and the general Hessenberg-QR kernel recomputes it.
 #pragma once
@@ -292,54 +293,67 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
     double* Bout = a.beam ? a.Bv + item * 2 * N : nullptr;
     double dinv[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        dinv[i] = 0.5 * pd_rsqrt(a.w[i] * a.mu[i]);
-        Kout[i] = k[i];
+    for (int i = 0; i < N; ++i) dinv[i] = 0.5 * pd_rsqrt(a.w[i] * a.mu[i]);
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+        pd_d2 k2;
+        k2.x = k[i];
+        k2.y = k[i + 1];
+        *reinterpret_cast<pd_d2*>(Kout + i) = k2;
     }
+    // Row by row from the bottom, V^ = L^-T W written over W in place: row r of U^ needs rows <= r of W (still
+    // untouched), row r of V^ needs rows > r of V^ (already in place).  A finished row of Gp / Gm is 8 N bytes of
+    // the lane's own block and leaves as 256-bit stores: the lanes of a warp are 16 N^2 bytes apart, so it is the
+    // number of store transactions, not their width, that the L1 -> L2 path sees (profiles/: 128 x 8-byte stores
+    // per lane made this phase 30 % of the kernel).
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-        double v[N], u[N];
+    for (int r = N - 1; r >= 0; --r) {
+        double ur[N], vr[N];
 #pragma unroll
-        for (int r = 0; r < N; ++r) {  // u = -(L w) / k_j
-            double s = 0.0;
-#pragma unroll
-            for (int c = 0; c <= r; ++c) s = fma(PD_L(r, c), W[c * N + j], s);
-            u[r] = -s * kinv[j];
+        for (int j = 0; j < N; ++j) {
+            ur[j] = 0.0;
+            vr[j] = W[r * N + j];
         }
 #pragma unroll
-        for (int r = N - 1; r >= 0; --r) {  // L^T v = w
-            double s = W[r * N + j];
+        for (int c = 0; c <= r; ++c) {
+            const double lrc = PD_L(r, c);
 #pragma unroll
-            for (int c = r + 1; c < N; ++c) s = fma(-PD_L(c, r), v[c], s);
-            v[r] = s * Li[(long)r * ps];
+            for (int j = 0; j < N; ++j) ur[j] = fma(lrc, W[c * N + j], ur[j]);
         }
 #pragma unroll
-        for (int r = 0; r < N; ++r) {
-            Gp_out[r * N + j] = (v[r] + u[r]) * dinv[r];
-            Gm_out[r * N + j] = (v[r] - u[r]) * dinv[r];
+        for (int c = r + 1; c < N; ++c) {
+            const double lcr = PD_L(c, r);
+#pragma unroll
+            for (int j = 0; j < N; ++j) vr[j] = fma(-lcr, W[c * N + j], vr[j]);
+        }
+        const double li = Li[(long)r * ps];
+        double gp[N], gm[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const double v = vr[j] * li, u = -ur[j] * kinv[j];
+            W[r * N + j] = v;
+            gp[j] = (v + u) * dinv[r];
+            gm[j] = (v - u) * dinv[r];
+        }
+#pragma unroll
+        for (int j = 0; j < N; j += 4) {
+            pd_store4(Gp_out + r * N + j, gp[j], gp[j + 1], gp[j + 2], gp[j + 3]);
+            pd_store4(Gm_out + r * N + j, gm[j], gm[j + 1], gm[j + 2], gm[j + 3]);
         }
     }
 
-    // helper products with the factors:  V^ x = L^-T (W x),  U^ x = -L (W (x / k))
+    // helper products with the factors (W now holds V^):  V^ x,   U^ x = -L L^T V^ (x / k)
     auto apply_V = [&](const double (&x)[N], double (&out)[N]) {
-        double y[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) {
             double s = 0.0;
 #pragma unroll
             for (int c = 0; c < N; ++c) s = fma(W[r * N + c], x[c], s);
-            y[r] = s;
-        }
-#pragma unroll
-        for (int r = N - 1; r >= 0; --r) {
-            double s = y[r];
-#pragma unroll
-            for (int c = r + 1; c < N; ++c) s = fma(-PD_L(c, r), out[c], s);
-            out[r] = s * Li[(long)r * ps];
+            out[r] = s;
         }
     };
     auto apply_U = [&](const double (&x)[N], double (&out)[N]) {
-        double y[N];
+        double y[N], z[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) {
             double s = 0.0;
@@ -348,10 +362,17 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
             y[r] = s;
         }
 #pragma unroll
+        for (int r = 0; r < N; ++r) {  // z = L^T y
+            double s = 0.0;
+#pragma unroll
+            for (int c = r; c < N; ++c) s = fma(PD_L(c, r), y[c], s);
+            z[r] = s;
+        }
+#pragma unroll
         for (int r = 0; r < N; ++r) {
             double s = 0.0;
 #pragma unroll
-            for (int c = 0; c <= r; ++c) s = fma(PD_L(r, c), y[c], s);
+            for (int c = 0; c <= r; ++c) s = fma(PD_L(r, c), z[c], s);
             out[r] = -s;
         }
     };
@@ -369,13 +390,21 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
             for (int c = r; c < N; ++c) s = fma(PD_L(c, r), rp[(long)c * ps], s);
             z[r] = s;
         }
+        double zz[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) {  // zz = L z = S r
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c <= r; ++c) s = fma(PD_L(r, c), z[c], s);
+            zz[r] = s;
+        }
         const double mu0b = a.colp[(long)b * PD_NCOLP + PD_COL_MU0];
         const double m2 = 1.0 / (mu0b * mu0b);
 #pragma unroll
-        for (int j = 0; j < N; ++j) {  // c = diag(1/(1/mu0^2 - k^2)) W^T z
+        for (int j = 0; j < N; ++j) {  // c = diag(1/(1/mu0^2 - k^2)) (V^)^-1 r,  (V^)^-1 = W^T L^T = V^T L L^T
             double s = 0.0;
 #pragma unroll
-            for (int r = 0; r < N; ++r) s = fma(W[r * N + j], z[r], s);
+            for (int r = 0; r < N; ++r) s = fma(W[r * N + j], zz[r], s);
             cvec[j] = s / (m2 - k[j] * k[j]);
         }
         apply_V(cvec, ph);  // p^ = V^ c
@@ -388,27 +417,31 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
             for (int c = r; c < N; ++c) s = fma(PD_L(c, r), ph[c], s);
             lt[r] = s;
         }
+        double bt[N], bb[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) {
             double s = 0.0;
 #pragma unroll
             for (int c = 0; c <= r; ++c) s = fma(PD_L(r, c), lt[c], s);
             const double qh = mu0b * (xd[(long)r * ps] - s);
-            Bout[r] = (ph[r] + qh) * dinv[r];       // dinv carries the factor 1/2
-            Bout[N + r] = (ph[r] - qh) * dinv[r];
+            bt[r] = (ph[r] + qh) * dinv[r];       // dinv carries the factor 1/2
+            bb[r] = (ph[r] - qh) * dinv[r];
+        }
+#pragma unroll
+        for (int r = 0; r < N; r += 2) {
+            pd_d2 t2, b2;
+            t2.x = bt[r]; t2.y = bt[r + 1];
+            b2.x = bb[r]; b2.y = bb[r + 1];
+            *reinterpret_cast<pd_d2*>(Bout + r) = t2;
+            *reinterpret_cast<pd_d2*>(Bout + N + r) = b2;
         }
     }
 
     if (thermal) {
-        // y = -k * W^T L^-1 (D / mu),  D_i / mu_i = sqrt(w_i / mu_i)
+        // y = -k * W^T L^-1 (D / mu) = -k * V^T (D / mu)   (W^T = V^T L),  D_i / mu_i = sqrt(w_i / mu_i)
         double f[N], y1[N];
 #pragma unroll
-        for (int r = 0; r < N; ++r) {  // forward substitution L f = D/mu
-            double s = sqrt(a.w[r] / a.mu[r]);
-#pragma unroll
-            for (int c = 0; c < r; ++c) s = fma(-PD_L(r, c), f[c], s);
-            f[r] = s * Li[(long)r * ps];
-        }
+        for (int r = 0; r < N; ++r) f[r] = sqrt(a.w[r] / a.mu[r]);
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             double s = 0.0;
@@ -438,9 +471,14 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
             apply_V(dm, vv);
             apply_U(sp, uu);
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                dout[q * 2 * N + i] = (vv[i] + uu[i]) * dinv[i];      // Gp t- - Gm t+
-                dout[q * 2 * N + N + i] = (vv[i] - uu[i]) * dinv[i];  // Gm t- - Gp t+
+            for (int i = 0; i < N; i += 2) {
+                pd_d2 t2, b2;
+                t2.x = (vv[i] + uu[i]) * dinv[i];              // Gp t- - Gm t+
+                t2.y = (vv[i + 1] + uu[i + 1]) * dinv[i + 1];
+                b2.x = (vv[i] - uu[i]) * dinv[i];              // Gm t- - Gp t+
+                b2.y = (vv[i + 1] - uu[i + 1]) * dinv[i + 1];
+                *reinterpret_cast<pd_d2*>(dout + q * 2 * N + i) = t2;
+                *reinterpret_cast<pd_d2*>(dout + q * 2 * N + N + i) = b2;
             }
         }
     }
