@@ -76,6 +76,32 @@ PD_HD void pd_store4(double* p, double a, double b, double c, double d) {
 #endif
 }
 
+// four consecutive doubles, 32-byte aligned, read once (streaming: not kept in L1) with one 256-bit load
+PD_HD void pd_load4_stream(const double* p, double (&v)[4]) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+                 : "l"(p));
+#else
+    v[0] = p[0];
+    v[1] = p[1];
+    v[2] = p[2];
+    v[3] = p[3];
+#endif
+}
+
+// same width through the coherent path (data written earlier by this kernel)
+PD_HD void pd_load4(const double* p, double (&v)[4]) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+#else
+    v[0] = p[0];
+    v[1] = p[1];
+    v[2] = p[2];
+    v[3] = p[3];
+#endif
+}
+
 // 1/sqrt(x), x > 0 finite: hardware seed (MUFU.RSQ64H) + two Newton steps (about 1 ulp)
 PD_HD double pd_rsqrt(double x) {
 #if defined(__CUDA_ARCH__)

@@ -71,12 +71,28 @@ PD_HD void pd_mode_at(const Grp& g, const PdEval& a, int b, int m, int l, double
     const double* dth = (a.iso && m == 0) ? a.st.dth + ((long)b * a.L + l) * a.Ns * n2 : nullptr;
     for (int i = lane; i < n; i += Grp::size) {
         double top = 0.0, bot = 0.0;
-        for (int j = 0; j < n; ++j) {
-            const double gp = Gp[i * n + j], gm = Gm[i * n + j];
-            top = fma(gp, ev[j], top);
-            top = fma(gm, ev[n + j], top);
-            bot = fma(gm, ev[j], bot);
-            bot = fma(gp, ev[n + j], bot);
+        if (NC > 0 && NC % 4 == 0) {  // G is read exactly once per query point: 256-bit streaming loads of the two rows
+#pragma unroll
+            for (int j = 0; j < (NC > 0 ? NC : 4); j += 4) {
+                double gp[4], gm[4];
+                pd_load4_stream(Gp + i * n + j, gp);
+                pd_load4_stream(Gm + i * n + j, gm);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    top = fma(gp[e], ev[j + e], top);
+                    top = fma(gm[e], ev[n + j + e], top);
+                    bot = fma(gm[e], ev[j + e], bot);
+                    bot = fma(gp[e], ev[n + j + e], bot);
+                }
+            }
+        } else {
+            for (int j = 0; j < n; ++j) {
+                const double gp = Gp[i * n + j], gm = Gm[i * n + j];
+                top = fma(gp, ev[j], top);
+                top = fma(gm, ev[n + j], top);
+                bot = fma(gm, ev[j], bot);
+                bot = fma(gp, ev[n + j], bot);
+            }
         }
         if (Bv) {
             top = fma(Bv[i], eb, top);

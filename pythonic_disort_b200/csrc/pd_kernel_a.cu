@@ -9,6 +9,16 @@ __global__ void k_stage_a(PdStageA a, const double* __restrict__ ptab, int items
     extern __shared__ double smem[];
     const int m = blockIdx.y;
     const int n = NC > 0 ? NC : a.N, nm = a.NLeg - m;
+    if (a.only_flagged) {  // fallback pass after the symmetric kernel: leave at once unless an item of this CTA is flagged
+        const int gi0 = threadIdx.x / LANES;
+        const long it0 = (long)blockIdx.x * items_per_cta + gi0;
+        bool flagged = false;
+        if (gi0 < items_per_cta && it0 < (long)a.B * a.L && (threadIdx.x % LANES) == 0) {
+            const double k0 = a.K[(((it0 / a.L) * a.NF + m) * a.L + it0 % a.L) * n];
+            flagged = !(k0 == k0);
+        }
+        if (!__syncthreads_or(flagged)) return;
+    }
     double* Q = smem;  // [nm][n] scaled Legendre table of this mode
     for (int idx = threadIdx.x; idx < nm * n; idx += blockDim.x) {
         const int i = idx % n;

@@ -483,10 +483,13 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
             if (l >= 0) {
                 const double* h = hbase + (long)l * F::HIST_PER_LAYER;
 #pragma unroll
-                for (int cc = 0; cc < SEG; cc += 2) {
-                    const pd_d2 v2 = *reinterpret_cast<const pd_d2*>(h + cc);
-                    mrow[u][cc] = v2.x;
-                    mrow[u][cc + 1] = v2.y;
+                for (int cc = 0; cc < SEG; cc += 4) {  // SEG = 8 or 32 doubles, 32-byte aligned: 256-bit loads
+                    double v4[4];
+                    pd_load4(h + cc, v4);
+                    mrow[u][cc] = v4[0];
+                    mrow[u][cc + 1] = v4[1];
+                    mrow[u][cc + 2] = v4[2];
+                    mrow[u][cc + 3] = v4[3];
                 }
                 zj[u] = (hh == 0) ? hist[(long)l * F::HIST_PER_LAYER + N2 * N2 + jr] : 0.0;
                 if (l - 2 * PF >= 0)  // the chunk after next: from HBM into L2
