@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
     os.environ.setdefault(_v, "1")
 
+import concurrent.futures  # noqa: E402
+
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
@@ -151,6 +153,7 @@ def run_gpu(args):
     import pythonic_disort_b200 as pd
     from pythonic_disort_b200 import _lib, api
 
+    warnings.simplefilter("ignore")  # the ensembles trip the reference's "close to 1" warnings by design
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -195,33 +198,58 @@ def run_gpu(args):
     phi_dev = torch.as_tensor(phi, device=dev) if phi is not None else None
     mu_user = ens.get("mu_user")  # config 5: intensities at user polar angles (row f1)
 
+    def one_chunk(a, kw, tau_eval, to_host, lo):
+        """One pydisort() call + evaluation for columns [lo, lo + chunk); returns bytes copied (h2d, d2h)."""
+        h2d = d2h = 0
+        hi = min(B, lo + chunk)
+        ca = [split(x, lo, hi) for x in a]
+        ck = {k: ([split(m, lo, hi) for m in v] if k == "BDRF_Fourier_modes" else split(v, lo, hi))
+              for k, v in kw.items()}
+        te = tau_eval[lo:hi]
+        if to_host:  # public API on (pinned) host buffers: pydisort copies in, the output functions copy out
+            h2d += sum(x.numel() * 8 for x in ca if isinstance(x, torch.Tensor)) + te.numel() * 8
+            h2d += sum(v.numel() * 8 for v in ck.values() if isinstance(v, torch.Tensor))
+            h2d += sum(m.numel() * 8 for m in ck.get("BDRF_Fourier_modes", []) if isinstance(m, torch.Tensor))
+        out = pd.pydisort(*ca, **ck)
+        Fp = out[1](te)
+        Fm, Fd = out[2](te)
+        if want_u and mu_user is not None:
+            uu = pd.subroutines.interpolate(out[4])(mu_user, te, phi if to_host else phi_dev)
+        else:
+            uu = out[4](te, phi if to_host else phi_dev) if want_u else None
+        if to_host:  # host inputs -> the API returned NumPy arrays (device->host copies already done)
+            assert isinstance(Fp, np.ndarray)
+            d2h += (Fp.size + Fm.size + Fd.size + (uu.size if want_u else 0)) * 8
+        del out
+        return h2d, d2h
+
+    # End-to-end arm: the chunks are independent pydisort() calls, so a caller pipelines them -- two host threads,
+    # each on its own CUDA stream (the API launches on torch's current stream), so that the host<->device copies of
+    # one chunk overlap the kernels of the other.  Everything stays inside the timed region.
+    e2e_streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    pool = concurrent.futures.ThreadPoolExecutor(max_workers=len(e2e_streams))
+
+    def chunk_on_stream(k, a, kw, tau_eval, lo):
+        torch.cuda.set_device(dev)
+        with torch.cuda.stream(e2e_streams[k]):
+            res = one_chunk(a, kw, tau_eval, True, lo)
+            e2e_streams[k].synchronize()
+        return res
+
     def step(a, kw, tau_eval, to_host):
         """The hot path over all columns, chunk by chunk; returns bytes copied (h2d, d2h)."""
-        h2d = d2h = 0
-        for lo in range(0, B, chunk):
-            hi = min(B, lo + chunk)
-            ca = [split(x, lo, hi) for x in a]
-            ck = {k: ([split(m, lo, hi) for m in v] if k == "BDRF_Fourier_modes" else split(v, lo, hi))
-                  for k, v in kw.items()}
-            te = tau_eval[lo:hi]
-            if to_host:  # public API on (pinned) host buffers: pydisort copies in, the output functions copy out
-                h2d += sum(x.numel() * 8 for x in ca if isinstance(x, torch.Tensor)) + te.numel() * 8
-                h2d += sum(v.numel() * 8 for v in ck.values() if isinstance(v, torch.Tensor))
-                h2d += sum(m.numel() * 8 for m in ck.get("BDRF_Fourier_modes", []) if isinstance(m, torch.Tensor))
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore")
-                out = pd.pydisort(*ca, **ck)
-                Fp = out[1](te)
-                Fm, Fd = out[2](te)
-                if want_u and mu_user is not None:
-                    uu = pd.subroutines.interpolate(out[4])(mu_user, te, phi if to_host else phi_dev)
-                else:
-                    uu = out[4](te, phi if to_host else phi_dev) if want_u else None
-            if to_host:  # host inputs -> the API returned NumPy arrays (device->host copies already done)
-                assert isinstance(Fp, np.ndarray)
-                d2h += (Fp.size + Fm.size + Fd.size + (uu.size if want_u else 0)) * 8
-            del out
-        return h2d, d2h
+        starts = list(range(0, B, chunk))
+        if to_host and len(starts) > 1:
+            cur = torch.cuda.current_stream(dev)
+            for st_ in e2e_streams:
+                st_.wait_stream(cur)
+            futs = [pool.submit(chunk_on_stream, i % len(e2e_streams), a, kw, tau_eval, lo) for i, lo in enumerate(starts)]
+            res = [f.result() for f in futs]
+            for st_ in e2e_streams:
+                cur.wait_stream(st_)
+        else:
+            res = [one_chunk(a, kw, tau_eval, to_host, lo) for lo in starts]
+        return sum(r[0] for r in res), sum(r[1] for r in res)
 
     def timed(nsteps, fn):
         if world > 1:

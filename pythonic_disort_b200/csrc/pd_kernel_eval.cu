@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(256) k_nt_tab(PdEval a, PdNT nt, const double*
     double* oth = own + (long)ntau * n2;     // [ntau][n2]
     double* chi = oth + (long)ntau * n2;     // [ntau][n]
     double* tsl = chi + (long)ntau * n;      // [ntau] scaled optical depth of the level
-    int* lay = reinterpret_cast<int*>(tsl + ntau);  // [ntau] its layer
+    double* termP = tsl + ntau;              // [n][L] terms and decay factors of the TMS layer scans
+    double* termN = termP + n * L;
+    double* decay = termN + n * L;
+    int* lay = reinterpret_cast<int*>(decay + n * L);  // [ntau] layer of the level
     const double* cp = a.st.colp + (long)b * PD_NCOLP;
     const double mu0 = cp[PD_COL_MU0], I0 = cp[PD_COL_I0];
     const double* taus = a.st.taus + (long)b * (L + 1);
@@ -125,14 +128,29 @@ __global__ void __launch_bounds__(256) k_nt_tab(PdEval a, PdNT nt, const double*
     for (int i = threadIdx.x; i < NA; i += blockDim.x) imsc[i] = 0.0;
     const int warp = threadIdx.x >> 5;
     __syncthreads();
-    if (warp == 0) {
-        SubWarp<32> g;
-        if (L > 1) pd_tms_scans(g, a, b, Rpos, Rneg);
-    } else if (warp == 1) {
+    if (warp == 1) {
         SubWarp<32> g;
         pd_ims_setup(g, a, nt, b, imsc, imsv);
     } else {
-        const int tid = threadIdx.x - 64, nth = blockDim.x - 64;
+        const int tid = threadIdx.x - (warp > 1 ? 32 : 0), nth = blockDim.x - 32;
+        // terms of the TMS layer scans (pd_tms_scans, same expressions): the exponentials of all (stream, layer)
+        // pairs in parallel, so that the sequential part below is one FMA per layer
+        const double* scl = a.st.scale_tau + (long)b * L;
+        for (int idx = tid; idx < n * L; idx += nth) {
+            const int i = idx / L, r = idx - i * L;
+            const double mu = a.st.mu_nodes[i], mi = 1.0 / mu;
+            const double dt = taus[r + 1] - taus[r];
+            double tp = -expm1(-dt * (mi + 1.0 / mu0)) * exp(-taus[r] / mu0);
+            if (a.anti) tp *= mu / scl[r];
+            const double dec = exp(-dt * mi);
+            const double th = dt * (mi - 1.0 / mu0);
+            const double em1 = expm1(-fabs(th));
+            double tn = (th >= 0.0) ? -em1 * exp(-taus[r + 1] / mu0) : em1 * dec * exp(-taus[r] / mu0);
+            if (a.anti) tn *= -mu / scl[r];
+            termP[idx] = tp;
+            termN[idx] = tn;
+            decay[idx] = dec;
+        }
         for (int idx = tid; idx < L * NA; idx += nth) {
             const int l = idx / NA, k = idx - l * NA;
             double v = 0.0;
@@ -149,6 +167,27 @@ __global__ void __launch_bounds__(256) k_nt_tab(PdEval a, PdNT nt, const double*
             const int l = pd_locate(a.st.tau + (long)b * L, L, tq);
             lay[t] = l;
             tsl[t] = pd_scaled_tau(a, b, l, tq);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * n && L > 1) {  // the scans themselves: Rpos by lanes 0..n-1 (bottom up), Rneg by lanes n..2n-1
+        const int i = threadIdx.x % n;
+        if (threadIdx.x < n) {
+            double acc = 0.0;
+            Rpos[i * L + (L - 1)] = 0.0;
+            for (int l = L - 2; l >= 0; --l) {
+                const int r = l + 1;
+                acc = (l == L - 2) ? termP[i * L + r] : fma(acc, decay[i * L + r], termP[i * L + r]);
+                Rpos[i * L + l] = acc;
+            }
+        } else {
+            double acc = 0.0;
+            Rneg[i * L] = 0.0;
+            for (int l = 1; l < L; ++l) {
+                const int r = l - 1;
+                acc = (l == 1) ? termN[i * L + r] : fma(acc, decay[i * L + r], termN[i * L + r]);
+                Rneg[i * L + l] = acc;
+            }
         }
     }
     __syncthreads();
@@ -333,7 +372,7 @@ int pd_eval_u(const pd_config* cfg, const pd_state* st, const double* tau_q, int
         // tabulated kernel for NLeg_all <= 32 (registers hold P_k(nu)); recurrence kernel otherwise or on request
         const char* env = getenv("PD_NT_RECURRENCE");
         constexpr int NA = 32;
-        const size_t smt = (size_t)(2 * a.N * a.L + NA + 2 + NA + 2 + (size_t)a.L * NA + (size_t)ntau * (5 * a.N + 1) +
+        const size_t smt = (size_t)(5 * a.N * a.L + NA + 2 + NA + 2 + (size_t)a.L * NA + (size_t)ntau * (5 * a.N + 1) +
                                     (ntau + 1) / 2 + 2) * 8;
         if (a.NLeg_all <= NA && 2 * a.N * nphi <= 256 && smt <= PD_SMEM_MAX_CTA && !(env && env[0] == '1')) {
             e = cudaFuncSetAttribute(k_nt_tab<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smt);
