@@ -96,7 +96,12 @@ int pd_launch_stage_a(const PdStageA& a_in, const double* ptab, cudaStream_t st)
     const int item_doubles = (pd_stage_a_item_doubles(N, a.NLeg) + 1) & ~1;
     const size_t qbytes = (size_t)((a.NLeg * N + 1) & ~1) * 8;
     int ipc = 128 / lanes;
-    while (ipc > 1 && qbytes + (size_t)ipc * item_doubles * 8 > 96 * 1024) ipc >>= 1;
+    size_t cta_budget = 48 * 1024;  // shared memory per CTA: four resident CTAs pack the SM better than two when an item needs ~10 KB (N = 16; measured 439 -> 355 ms)
+    if (const char* e = getenv("PD_STAGE_A_CTA_KB")) {
+        const int v = atoi(e);
+        if (v >= 8 && v <= 200) cta_budget = (size_t)v * 1024;
+    }
+    while (ipc > 1 && qbytes + (size_t)ipc * item_doubles * 8 > cta_budget) ipc >>= 1;
     const int threads = ipc * lanes < 32 ? 32 : ipc * lanes;
     const size_t smem = qbytes + (size_t)ipc * item_doubles * 8;
     if (smem > PD_SMEM_MAX_CTA) return -22;
