@@ -184,6 +184,17 @@ int pd_eval_u(const pd_config* cfg, const pd_state* st, const double* tau_q, int
  *   out[b][o][m] = sum_i wts[o][i] * u[b][i][m],   m < M  (M = ntau * nphi, or ntau for u0). */
 int pd_interp_mu(int B, int n2, long M, int nmu, const double* wts, const double* u, double* out, void* stream);
 
+/* Thermal-source inputs on the device.
+ * pd_planck_band   : PythonicDISORT.subroutines.blackbody_contrib_to_BCs (subroutines.py:354-377), i.e. the integral of
+ *                    Planck(T, nu) (:322-350) over [wvnmlo, wvnmhi], for n temperatures T[n] -> out[n]  (W m^-2).
+ * pd_s_poly_coeffs : generate_s_poly_coeffs (subroutines.py:413-454) for B columns: tau[B][L] (lower boundaries),
+ *                    temper[B][L+1] (level temperatures, top to bottom) -> s_poly[B][L][2] (intercept, slope), the
+ *                    `s_poly_coeffs` input of pydisort().
+ * gl16[32]: the 16 Gauss-Legendre nodes on [-1, 1] followed by their weights (numpy.polynomial.legendre.leggauss(16)). */
+int pd_planck_band(long n, const double* T, double wvnmlo, double wvnmhi, const double* gl16, double* out, void* stream);
+int pd_s_poly_coeffs(int B, int L, const double* tau, const double* temper, double wvnmlo, double wvnmhi,
+                     const double* gl16, double* s_poly, void* stream);
+
 /* FP64 FMA throughput probe (one launch of dependent-free DFMA chains); used
  * by bench.py to measure the FP64 roofline denominator on the box.
  * Returns the number of FLOPs the launch performs; time it with CUDA events. */

@@ -229,6 +229,52 @@ class _Solution:
         return u, ulast, ph, ntau, nphi
 
 
+_gl16_cache = {}
+
+
+def _gl16(dev):
+    """16-point Gauss-Legendre rule (nodes then weights) on the device, for the Planck band integrals."""
+    if dev not in _gl16_cache:
+        x, w = np.polynomial.legendre.leggauss(16)
+        _gl16_cache[dev] = torch.as_tensor(np.concatenate([x, w]), dtype=_F64, device=dev)
+    return _gl16_cache[dev]
+
+
+def planck_band(T, WVNMLO, WVNMHI):
+    """Band-integrated blackbody emission of every temperature in the tensor ``T`` (any shape), on the device
+    (row f2; ``subroutines.blackbody_contrib_to_BCs``, subroutines.py:354-377)."""
+    lib, dev = _backend()
+    Tt = T.to(device=dev, dtype=_F64).contiguous()
+    out = torch.empty_like(Tt)
+    if Tt.numel():
+        rc = lib.pd_planck_band(Tt.numel(), _ptr(Tt), float(WVNMLO), float(WVNMHI), _ptr(_gl16(dev)), _ptr(out),
+                                _stream(dev))
+        if rc != 0:
+            raise RuntimeError(f"libpydisort_b200: pd_planck_band failed with code {rc}")
+    return out
+
+
+def s_poly_coeffs(tau_arr, TEMPER, WVNMLO, WVNMHI):
+    """``generate_s_poly_coeffs`` (subroutines.py:413-454) for a batch: ``tau_arr`` [B, L] (or [L]), ``TEMPER``
+    [B, L+1] (or [L+1]) tensors -> ``s_poly_coeffs`` [B, L, 2] (or [L, 2]) on the device, ready for ``pydisort``."""
+    lib, dev = _backend()
+    tau = tau_arr.to(device=dev, dtype=_F64)
+    tem = TEMPER.to(device=dev, dtype=_F64)
+    single = tau.ndim == 1
+    if single:
+        tau, tem = tau[None], tem[None]
+    if tau.ndim != 2 or tem.ndim != 2 or tem.shape[0] != tau.shape[0] or tem.shape[1] != tau.shape[1] + 1:
+        raise ValueError("Missing temperature specification at some boundaries / interfaces.")
+    tau, tem = tau.contiguous(), tem.contiguous()
+    B, L = tau.shape
+    out = torch.empty((B, L, 2), dtype=_F64, device=dev)
+    rc = lib.pd_s_poly_coeffs(B, L, _ptr(tau), _ptr(tem), float(WVNMLO), float(WVNMHI), _ptr(_gl16(dev)), _ptr(out),
+                              _stream(dev))
+    if rc != 0:
+        raise RuntimeError(f"libpydisort_b200: pd_s_poly_coeffs failed with code {rc}")
+    return out[0] if single else out
+
+
 def barycentric_weight_matrix(mu, N):
     """Weight matrix [nmu, 2N] of ``subroutines.interpolate`` (subroutines.py:614-705): row o holds the barycentric
     Lagrange weights of the N Gauss-Legendre streams of the hemisphere of ``mu[o]`` (``mu > 0``: the upward streams

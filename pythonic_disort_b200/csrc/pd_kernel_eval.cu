@@ -2,6 +2,7 @@
 #include <stdlib.h>
 
 #include "pd_launch.h"
+#include "pd_inputs.cuh"
 
 // ============================================================================
 // evaluation kernels
@@ -293,7 +294,51 @@ __global__ void k_interp_mu(int n2, long M, int nmu, const double* __restrict__ 
         if (o0 + o < nmu) out[(b * nmu + o0 + o) * M + mm] = acc[o];
 }
 
+// ---- thermal-source inputs (row f2) ----
+__global__ void k_planck_band(long n, const double* __restrict__ T, double wlo, double whi, const double* __restrict__ gl,
+                              double* __restrict__ out) {
+    __shared__ double g[32];
+    if (threadIdx.x < 32) g[threadIdx.x] = gl[threadIdx.x];
+    __syncthreads();
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = pd_planck_band_value(T[i], wlo, whi, g);
+}
+
+// one CTA per column: band emission at the L + 1 levels, then the spline coefficients of the L layers
+__global__ void k_s_poly_coeffs(int L, const double* __restrict__ tau, const double* __restrict__ temper, double wlo, double whi,
+                                const double* __restrict__ gl, double* __restrict__ s_poly) {
+    extern __shared__ double smem[];  // [32] rule, [L + 1] emission
+    double* g = smem;
+    double* em = smem + 32;
+    const long b = blockIdx.x;
+    if (threadIdx.x < 32) g[threadIdx.x] = gl[threadIdx.x];
+    __syncthreads();
+    for (int lv = threadIdx.x; lv <= L; lv += blockDim.x) em[lv] = pd_planck_band_value(temper[b * (L + 1) + lv], wlo, whi, g);
+    __syncthreads();
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        const double x0 = (l == 0) ? 0.0 : tau[b * L + l - 1], x1 = tau[b * L + l];
+        pd_linear_segment(x0, em[l], x1, em[l + 1], s_poly + (b * L + l) * 2);
+    }
+}
+
 extern "C" {
+
+int pd_planck_band(long n, const double* T, double wvnmlo, double wvnmhi, const double* gl16, double* out, void* stream) {
+    if (n < 1 || !T || !gl16 || !out) return -50;
+    const int threads = 128;
+    const long blocks = (n + threads - 1) / threads;
+    if (blocks > 2147483647L) return -51;
+    k_planck_band<<<(unsigned)blocks, threads, 0, pd_stream(stream)>>>(n, T, wvnmlo, wvnmhi, gl16, out);
+    return (int)cudaGetLastError();
+}
+
+int pd_s_poly_coeffs(int B, int L, const double* tau, const double* temper, double wvnmlo, double wvnmhi, const double* gl16,
+                     double* s_poly, void* stream) {
+    if (B < 1 || L < 1 || !tau || !temper || !gl16 || !s_poly) return -50;
+    const int threads = (L + 1 <= 32) ? 32 : (L + 1 <= 64 ? 64 : 128);
+    k_s_poly_coeffs<<<B, threads, (size_t)(32 + L + 1) * 8, pd_stream(stream)>>>(L, tau, temper, wvnmlo, wvnmhi, gl16, s_poly);
+    return (int)cudaGetLastError();
+}
 
 int pd_interp_mu(int B, int n2, long M, int nmu, const double* wts, const double* u, double* out, void* stream) {
     if (B < 1 || n2 < 2 || (n2 & 1) || M < 1 || nmu < 1 || !wts || !u || !out) return -40;

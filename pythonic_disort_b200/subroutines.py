@@ -137,8 +137,19 @@ def Planck(T, WVNM):
     return np.squeeze(out)[()]
 
 
+def _is_tensor(x):
+    return hasattr(x, "detach") and hasattr(x, "data_ptr")
+
+
 def blackbody_contrib_to_BCs(T, WVNMLO, WVNMHI, **kwargs):
-    """Band-integrated blackbody emission of a boundary (subroutines.py:354-377)."""
+    """Band-integrated blackbody emission of a boundary (subroutines.py:354-377).
+
+    A torch tensor of temperatures (any shape, e.g. one per column) is integrated on the GPU (``pd_planck_band``,
+    fixed Gauss-Legendre panels in ``h c nu / k T``) and a tensor of the same shape comes back; anything else takes
+    the reference's route (``scipy.integrate.quad_vec`` on the host)."""
+    if _is_tensor(T):
+        from . import api
+        return api.planck_band(T, WVNMLO, WVNMHI)
     return np.squeeze(scipy.integrate.quad_vec(lambda w: Planck(T, w), WVNMLO, WVNMHI, **kwargs)[0])
 
 
@@ -160,8 +171,25 @@ def linear_spline_coefficients(x, y, check_inputs=True):
 
 def generate_s_poly_coeffs(tau_arr, TEMPER, WVNMLO, WVNMHI, **kwargs):
     """DISORT-equivalent linear-in-tau thermal source coefficients from level
-    temperatures (subroutines.py:413-454)."""
+    temperatures (subroutines.py:413-454).
+
+    Torch tensors ``tau_arr`` [B, NLayers] / ``TEMPER`` [B, NLayers + 1] (or the unbatched 1-D pair) are processed
+    on the GPU (``pd_s_poly_coeffs``) and the coefficients stay there, ready to be passed to ``pydisort`` as
+    ``s_poly_coeffs``; NumPy input takes the reference's host route (2-D input: one column per row)."""
+    if _is_tensor(tau_arr) or _is_tensor(TEMPER):
+        import torch
+        from . import api
+        return api.s_poly_coeffs(torch.as_tensor(tau_arr), torch.as_tensor(TEMPER), WVNMLO, WVNMHI)
     tau_arr = np.atleast_1d(tau_arr)
+    TEMPER = np.asarray(TEMPER, dtype=float)
+    if tau_arr.ndim == 2:  # batch on the host: one integration over all temperatures, one spline per column
+        if TEMPER.shape != (tau_arr.shape[0], tau_arr.shape[1] + 1):
+            raise ValueError("Missing temperature specification at some boundaries / interfaces.")
+        em = scipy.integrate.quad_vec(lambda w: Planck(TEMPER.ravel(), w), WVNMLO, WVNMHI, **kwargs)[0]
+        em = np.reshape(em, TEMPER.shape)
+        lev = np.concatenate([np.zeros((tau_arr.shape[0], 1)), tau_arr], axis=1)
+        slope = np.diff(em, axis=1) / np.diff(lev, axis=1)
+        return np.stack([em[:, :-1] - slope * lev[:, :-1], slope], axis=2)
     if not len(TEMPER) == len(tau_arr) + 1:
         raise ValueError("Missing temperature specification at some boundaries / interfaces.")
     levels = prepend(tau_arr, len(tau_arr), 0)

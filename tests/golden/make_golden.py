@@ -14,6 +14,8 @@ What it does
      quadrature nodes (that is all the solver ever asks of them);
   2. copies the Stamnes DISORT 4.0.99 result files the tests compare against
      (data, not code) to ``tests/golden/stamnes/``;
+  5. (``thermal``) runs the reference's ``blackbody_contrib_to_BCs`` / ``generate_s_poly_coeffs`` on fixed temperatures,
+     bands and atmospheres -> ``tests/golden/thermal_inputs.npz``;
   4. (``interpolate``) runs the reference's ``subroutines.interpolate`` on its own ``u`` / ``u0`` at the user
      polar angles of config 5 -> ``tests/golden/interpolate.npz``;
   3. runs the reference on fixed subsets of the three synthetic ensembles of
@@ -244,8 +246,25 @@ def run_interpolate():
     np.savez_compressed(os.path.join(HERE, "interpolate.npz"), **out)
 
 
+def run_thermal():
+    """Row f2: the reference's thermal-source helpers (subroutines.py:322-454) on fixed inputs: band emission for a
+    range of temperatures and bands (narrow, wide, far tail) and s_poly_coeffs for a few atmospheres."""
+    rng = np.random.default_rng(20260104)
+    T = np.concatenate([[0.0, 2.7, 50.0], np.linspace(150.0, 340.0, 24), [1000.0, 5800.0]])
+    bands = np.array([[999.0, 1000.0], [100.0, 110.0], [600.0, 700.0], [0.01, 50000.0], [2500.0, 2600.0], [10.0, 3000.0]])
+    em = np.array([ref_sub.blackbody_contrib_to_BCs(T, lo, hi) for lo, hi in bands])
+    ncol, L = 5, 12
+    tau = np.cumsum(rng.uniform(0.05, 2.0, (ncol, L)), axis=1)
+    temper = np.sort(rng.uniform(180.0, 310.0, (ncol, L + 1)), axis=1)
+    sp_bands = np.array([[999.0, 1000.0], [600.0, 700.0], [10.0, 3000.0]])
+    sp = np.array([[ref_sub.generate_s_poly_coeffs(tau[b], temper[b], lo, hi) for b in range(ncol)] for lo, hi in sp_bands])
+    np.savez_compressed(os.path.join(HERE, "thermal_inputs.npz"), T=T, bands=bands, emission=em, tau=tau, temper=temper,
+                        sp_bands=sp_bands, s_poly=sp)
+    print("thermal inputs:", em.shape, sp.shape)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["suite", "stamnes", "ensembles", "interpolate"]
+    what = sys.argv[1:] or ["suite", "stamnes", "ensembles", "interpolate", "thermal"]
     if "suite" in what:
         run_reference_suite()
     if "stamnes" in what:
@@ -254,3 +273,5 @@ if __name__ == "__main__":
         run_ensembles()
     if "interpolate" in what:
         run_interpolate()
+    if "thermal" in what:
+        run_thermal()

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include "../../pythonic_disort_b200/csrc/pd_eval.cuh"
+#include "../../pythonic_disort_b200/csrc/pd_inputs.cuh"
 #include "../../pythonic_disort_b200/csrc/pd_prologue.cuh"
 #include "../../pythonic_disort_b200/csrc/pd_stage_a.cuh"
 #include "../../pythonic_disort_b200/csrc/pd_stage_a_sym.cuh"
@@ -196,6 +197,24 @@ int pd_interp_mu(int B, int n2, long M, int nmu, const double* wts, const double
                 for (int i = 0; i < n2; ++i) acc = fma(wts[(long)o * n2 + i], u[(b * n2 + i) * M + m], acc);
                 out[(b * nmu + o) * M + m] = acc;
             }
+    return 0;
+}
+
+int pd_planck_band(long n, const double* T, double wlo, double whi, const double* gl16, double* out, void*) {
+    if (n < 1 || !T || !gl16 || !out) return -50;
+    for (long i = 0; i < n; ++i) out[i] = pd_planck_band_value(T[i], wlo, whi, gl16);
+    return 0;
+}
+
+int pd_s_poly_coeffs(int B, int L, const double* tau, const double* temper, double wlo, double whi, const double* gl16,
+                     double* s_poly, void*) {
+    if (B < 1 || L < 1 || !tau || !temper || !gl16 || !s_poly) return -50;
+    for (long b = 0; b < B; ++b)
+        for (int l = 0; l < L; ++l) {
+            const double e0 = pd_planck_band_value(temper[b * (L + 1) + l], wlo, whi, gl16);
+            const double e1 = pd_planck_band_value(temper[b * (L + 1) + l + 1], wlo, whi, gl16);
+            pd_linear_segment(l == 0 ? 0.0 : tau[b * L + l - 1], e0, tau[b * L + l], e1, s_poly + (b * L + l) * 2);
+        }
     return 0;
 }
 

@@ -117,3 +117,38 @@ def check_interpolate_vs_golden(pd_module, name, tol=1e-9):
     host = pd_module.subroutines.interpolate(plain)(mu, t, phi)
     np.testing.assert_allclose(got_u, host, rtol=1e-10, atol=1e-12 * np.max(np.abs(host)))
     return worst
+
+
+def check_thermal_inputs_vs_golden(pd_module, tol=1e-9):
+    """Row f2: band-integrated Planck emission and s_poly_coeffs from level temperatures through the C ABI
+    (pd_planck_band, pd_s_poly_coeffs) against the reference's quad_vec-based helpers
+    (tests/golden/thermal_inputs.npz).  The reference integrates to a relative 1e-8 only, so the bar is the usual
+    1e-9 of scale per output array, not per element."""
+    import torch
+    from pythonic_disort_b200 import api
+    sub = pd_module.subroutines
+    gold = np.load(os.path.join(golden_io.GOLDEN, "thermal_inputs.npz"))
+    dev = api._backend()[1]
+    worst = 0.0
+    T = torch.as_tensor(gold["T"], device=dev)
+    for (lo, hi), ref in zip(gold["bands"], gold["emission"]):
+        got = to_np(sub.blackbody_contrib_to_BCs(T, lo, hi))
+        assert got.shape == ref.shape
+        err = np.max(np.abs(got - ref)) / np.max(np.abs(ref))
+        assert err <= tol, ("emission", lo, hi, err)
+        big = np.abs(ref) > 1e-6 * np.max(np.abs(ref))  # pointwise where the value matters
+        assert np.max(np.abs(got[big] - ref[big]) / np.abs(ref[big])) <= 1e-7
+        worst = max(worst, err)
+    tau, tem = torch.as_tensor(gold["tau"], device=dev), torch.as_tensor(gold["temper"], device=dev)
+    for (lo, hi), ref in zip(gold["sp_bands"], gold["s_poly"]):
+        got = to_np(sub.generate_s_poly_coeffs(tau, tem, lo, hi))
+        assert got.shape == ref.shape
+        for k in range(2):
+            err = np.max(np.abs(got[..., k] - ref[..., k])) / np.max(np.abs(ref[..., k]))
+            assert err <= 10 * tol, ("s_poly", lo, hi, k, err)  # slopes difference two integrals accurate to 1e-8 each
+            worst = max(worst, err)
+        one = to_np(sub.generate_s_poly_coeffs(tau[1], tem[1], lo, hi))  # unbatched tensor call
+        np.testing.assert_array_equal(one, got[1])
+        host = sub.generate_s_poly_coeffs(gold["tau"], gold["temper"], lo, hi)  # NumPy input: host route, batched
+        np.testing.assert_allclose(host, ref, rtol=1e-7, atol=1e-9 * np.max(np.abs(ref)))
+    return worst

@@ -50,6 +50,24 @@ def test_interpolate_at_user_polar_angles_on_the_device(name):
     parity_suite.check_interpolate_vs_golden(pd, name)
 
 
+def test_thermal_source_inputs_on_the_device():
+    """Row f2 (subroutines.py:322-454): pd_planck_band / pd_s_poly_coeffs against the reference's helpers; the
+    coefficients stay on the device and feed pydisort() directly."""
+    import torch
+    parity_suite.check_thermal_inputs_vs_golden(pd)
+    ens = synthetic.make("lw", 32)
+    tau = torch.as_tensor(ens["args"][0], device="cuda")
+    temper = torch.linspace(210.0, 290.0, tau.shape[1] + 1, device="cuda", dtype=torch.float64).repeat(32, 1)
+    sp_dev = pd.subroutines.generate_s_poly_coeffs(tau, temper, 600.0, 700.0)
+    sp_host = pd.subroutines.generate_s_poly_coeffs(ens["args"][0], temper.cpu().numpy(), 600.0, 700.0)
+    kw = dict(ens["kwargs"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = pd.pydisort(*ens["args"], **{**kw, "s_poly_coeffs": sp_dev})[1](ens["tau_eval"])
+        b = pd.pydisort(*ens["args"], **{**kw, "s_poly_coeffs": sp_host})[1](ens["tau_eval"])
+    np.testing.assert_allclose(parity_suite.to_np(a), b, rtol=1e-7)
+
+
 @pytest.mark.parametrize("name,ncol,first", [("sw", 48, 1000), ("lw", 256, 5000), ("tp1", 6, 0), ("tp9c", 2, 0)])
 def test_ensembles_vs_live_oracle(name, ncol, first):
     from oracle import disort_oracle

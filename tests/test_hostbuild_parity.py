@@ -40,6 +40,10 @@ def test_interpolate_at_user_polar_angles(name):
     parity_suite.check_interpolate_vs_golden(pd, name)
 
 
+def test_thermal_source_inputs():
+    parity_suite.check_thermal_inputs_vs_golden(pd)
+
+
 def _counts(lib):
     import ctypes
     lib.pd_hostsim_count.restype = ctypes.c_long
