@@ -33,8 +33,6 @@ sys.path.insert(0, ROOT)
 for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
     os.environ.setdefault(_v, "1")
 
-import concurrent.futures  # noqa: E402
-
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
@@ -223,32 +221,81 @@ def run_gpu(args):
         del out
         return h2d, d2h
 
-    # End-to-end arm: the chunks are independent pydisort() calls, so a caller pipelines them -- two host threads,
-    # each on its own CUDA stream (the API launches on torch's current stream), so that the host<->device copies of
-    # one chunk overlap the kernels of the other.  Everything stays inside the timed region.
-    e2e_streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-    pool = concurrent.futures.ThreadPoolExecutor(max_workers=len(e2e_streams))
+    # End-to-end arm: a three-stage pipeline over the chunks, the way a caller with host data drives the public API:
+    # pinned host inputs -> device on a copy stream (one chunk ahead), pydisort() + output functions on device tensors
+    # on the compute stream, results -> pinned host buffers on a second copy stream.  The copies of one chunk overlap
+    # the kernels of its neighbours; every byte moved is inside the timed region.  (Two host threads on two streams do
+    # not achieve this: their kernels interleave and both reach the copy phase at the same time -- tools/e2e_overlap.py.)
+    h2d_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    host_out = {}  # (slot, name) -> pinned buffer, slot = chunk parity
 
-    def chunk_on_stream(k, a, kw, tau_eval, lo):
-        torch.cuda.set_device(dev)
-        with torch.cuda.stream(e2e_streams[k]):
-            res = one_chunk(a, kw, tau_eval, True, lo)
-            e2e_streams[k].synchronize()
-        return res
+    def to_device_async(x, cur):
+        if not isinstance(x, torch.Tensor):
+            return x
+        d = x.to(dev, non_blocking=True)
+        d.record_stream(cur)
+        return d
+
+    def step_e2e(a, kw, tau_eval):
+        cur = torch.cuda.current_stream(dev)
+        starts = list(range(0, B, chunk))
+        h2d = d2h = 0
+        staged, done = {}, {}
+
+        def stage(i):
+            lo, hi = starts[i], min(B, starts[i] + chunk)
+            with torch.cuda.stream(h2d_stream):
+                ca = [to_device_async(split(x, lo, hi), cur) for x in a]
+                ck = {k: ([to_device_async(split(m, lo, hi), cur) for m in v] if k == "BDRF_Fourier_modes"
+                          else to_device_async(split(v, lo, hi), cur)) for k, v in kw.items()}
+                te = to_device_async(tau_eval[lo:hi], cur)
+                ev = torch.cuda.Event()
+                ev.record(h2d_stream)
+            nbytes = sum(x.numel() * 8 for x in ca if isinstance(x, torch.Tensor)) + te.numel() * 8
+            nbytes += sum(v.numel() * 8 for v in ck.values() if isinstance(v, torch.Tensor))
+            nbytes += sum(m.numel() * 8 for m in ck.get("BDRF_Fourier_modes", []) if isinstance(m, torch.Tensor))
+            staged[i] = (ca, ck, te, ev, nbytes)
+
+        h2d_stream.wait_stream(cur)
+        stage(0)
+        for i in range(len(starts)):
+            if i + 1 < len(starts):
+                stage(i + 1)
+            ca, ck, te, ev, nbytes = staged.pop(i)
+            h2d += nbytes
+            cur.wait_event(ev)
+            out = pd.pydisort(*ca, **ck)
+            res = {"Fp": out[1](te)}
+            res["Fm"], res["Fd"] = out[2](te)
+            if want_u and mu_user is not None:
+                res["u"] = pd.subroutines.interpolate(out[4])(mu_user, te, phi_dev)
+            elif want_u:
+                res["u"] = out[4](te, phi_dev)
+            evc = torch.cuda.Event()
+            evc.record(cur)
+            if i - 2 in done:  # the pinned buffers of this parity are free once their previous copy has landed
+                done.pop(i - 2).synchronize()
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(evc)
+                for name, t in res.items():
+                    key = (i % 2, name)
+                    if key not in host_out or host_out[key].shape != t.shape:
+                        host_out[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                    t.record_stream(d2h_stream)
+                    host_out[key].copy_(t, non_blocking=True)
+                    d2h += t.numel() * 8
+                evd = torch.cuda.Event()
+                evd.record(d2h_stream)
+            done[i] = evd
+            del out, res
+        cur.wait_stream(d2h_stream)
+        return h2d, d2h
 
     def step(a, kw, tau_eval, to_host):
         """The hot path over all columns, chunk by chunk; returns bytes copied (h2d, d2h)."""
-        starts = list(range(0, B, chunk))
-        if to_host and len(starts) > 1:
-            cur = torch.cuda.current_stream(dev)
-            for st_ in e2e_streams:
-                st_.wait_stream(cur)
-            futs = [pool.submit(chunk_on_stream, i % len(e2e_streams), a, kw, tau_eval, lo) for i, lo in enumerate(starts)]
-            res = [f.result() for f in futs]
-            for st_ in e2e_streams:
-                cur.wait_stream(st_)
-        else:
-            res = [one_chunk(a, kw, tau_eval, to_host, lo) for lo in starts]
+        if to_host:
+            return step_e2e(a, kw, tau_eval)
+        res = [one_chunk(a, kw, tau_eval, False, lo) for lo in range(0, B, chunk)]
         return sum(r[0] for r in res), sum(r[1] for r in res)
 
     def timed(nsteps, fn):
