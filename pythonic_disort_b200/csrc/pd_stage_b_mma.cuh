@@ -35,6 +35,9 @@
 #ifndef PD_MMA_BCAST_SHFL
 #define PD_MMA_BCAST_SHFL 0  // pivot packet by warp shuffles (1) or through shared memory (0)
 #endif
+#ifndef PD_MMA_PFD
+#define PD_MMA_PFD 12        // L2 prefetch distance (layers) of the history in the back sweep
+#endif
 #ifndef PD_MMA_PF
 #define PD_MMA_PF 2          // layers of history in flight in the back sweep
 #endif
@@ -48,7 +51,9 @@ struct PdStageBMma {
     static constexpr int PS = RC + 4;           // stride of a published pivot row: 4 (mod 16) doubles, so that the
                                                 // operand loads of a half warp touch 16 distinct bank pairs
     static constexpr int BLK = NR * 4, PROW = 4 * PS, PKT = 2 * 8;
-    static constexpr int SMEM_FIXED = 2 * BLK + PROW + PKT + N * N + N2 + NR + NR / 2 + NR / 2;
+    static constexpr int RING = 3;              // layers of G / E / beam vector staged in shared memory (cp.async)
+    static constexpr int GL = 2 * N * N;        // doubles of one layer's two G blocks
+    static constexpr int SMEM_FIXED = 2 * BLK + PROW + PKT + N * N + N2 + NR + NR / 2 + NR / 2 + RING * (GL + N + N2);
     PD_HD static int smem_doubles(int L) { return (SMEM_FIXED + L + 1 + 1) & ~1; }
     static constexpr long HIST_PER_LAYER = (long)N2 * N2 + N2;  // M_l [2N][2N] row-major, z_l [2N]
     // per-slot scratch in global memory: the history of all layers, then exp(-k_l dtau*_l) [L][N] (kept out of shared
@@ -68,6 +73,14 @@ __device__ __forceinline__ double pd_rcp3(double x) {
     r = fma(r, fma(e, e, e), r);
     const double e2 = fma(-x, r, 1.0);  // off the chain when the seed is good to 2^-20; keeps full accuracy if it is not
     return fma(r, e2, r);
+}
+
+// 16 bytes global -> shared without passing through registers (L2 only: the source may have been written by this kernel)
+__device__ __forceinline__ void pd_cp_async16(double* dst_smem, const double* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void pd_cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 // D = A (8x4, row) * B (4x8, col) + D on the FP64 tensor cores
@@ -93,7 +106,10 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
     double* npOf = xs + N2;              // [NR] -1/pivot of a row slot that was a pivot row in this stage
     int* colOf = reinterpret_cast<int*>(npOf + NR);  // [NR] its pivot column, -1: none
     int* kOf = colOf + NR;               // [NR] index (0..3) of a row slot among the current block's pivots, -1: none
-    double* att = npOf + NR + NR / 2 + NR / 2;  // [L+1]   exp(-tau*_l / mu0)
+    double* gring = npOf + NR + NR / 2 + NR / 2;  // [RING][2][N][N] G blocks of layers l, l+1 (in use) and l+2 (in flight)
+    double* ering = gring + F::RING * F::GL;      // [RING][N]  exp(-k dtau*) of those layers
+    double* bring = ering + F::RING * N;          // [RING][2N] beam particular solution of those layers
+    double* att = bring + F::RING * N2;           // [L+1]   exp(-tau*_l / mu0)
     double* Eall = hist + (long)L * F::HIST_PER_LAYER;  // [L][N]  exp(-k_l dtau*_l), global scratch of this slot
 
     const long sys = (long)b * A.NF + m;
@@ -110,9 +126,19 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
     const double* bpos = A.bpos + ((long)b * A.NFb + (A.NFb > 1 ? m : 0)) * N;
     const double* bneg = A.bneg + ((long)b * A.NFb + (A.NFb > 1 ? m : 0)) * N;
 
-    auto Grow = [&](int l, int r, int half) -> const double* {  // the N entries G_l[r][half*N .. half*N+N)
+    // the N entries G_l[r][half*N .. half*N+N), from the shared-memory ring (layer l must be staged)
+    auto Grow = [&](int l, int r, int half) -> const double* {
         const int rb = r >= N;
-        return Gc + ((long)l * 2 + (rb ^ half)) * N * N + (r - rb * N) * N;
+        return gring + (l % F::RING) * F::GL + (rb ^ half) * N * N + (r - rb * N) * N;
+    };
+    // asynchronous copy of layer ll (G blocks, exp(-k dtau*), beam vector) into its ring slot
+    auto stage_layer = [&](int ll) {
+        const int sl = ll % F::RING;
+        const double* gsrc = Gc + (long)ll * F::GL;
+#pragma unroll
+        for (int ch = lane; ch < F::GL / 2; ch += 32) pd_cp_async16(gring + sl * F::GL + 2 * ch, gsrc + 2 * ch);
+        if (lane < N / 2) pd_cp_async16(ering + sl * N + 2 * lane, Eall + (long)ll * N + 2 * lane);
+        else if (Bc && lane >= 16 && lane < 16 + N) pd_cp_async16(bring + sl * N2 + 2 * (lane - 16), Bc + (long)ll * N2 + 2 * (lane - 16));
     };
     auto bit = [](mask_t mk, int s) -> bool { return (mk >> s) & (mask_t)1; };
     auto below = [](int s) -> mask_t { return ((mask_t)1 << s) - (mask_t)1; };
@@ -128,6 +154,10 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
     }
     if (beam)
         for (int ll = lane; ll <= L; ll += 32) att[ll] = exp(-taus[ll] / mu0);
+    __syncwarp();
+    stage_layer(0);
+    if (L > 1) stage_layer(1);
+    pd_cp_async_wait_all();
     __syncwarp();
 
     double c[RT][CT][2];  // accumulator tiles: row slot rt*8 + q, columns ct*8 + 2t + {0, 1}
@@ -149,8 +179,8 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
             const int nb = ct / NT8, cc0 = (ct % NT8) * 8 + 2 * t;
             pd_d2 v = *reinterpret_cast<const pd_d2*>(Grow(0, r, nb) + cc0);
             if (nb == 1) {
-                v.x *= Eall[cc0];
-                v.y *= Eall[cc0 + 1];
+                v.x *= ering[cc0];
+                v.y *= ering[cc0 + 1];
             }
             c[rt][ct][0] = v.x;
             c[rt][ct][1] = v.y;
@@ -162,7 +192,7 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
         double v = 0.0;
         if (slot < N) {
             v = have_b ? bneg[slot] : 0.0;
-            if (beam) v -= Bc[N + slot];
+            if (beam) v -= bring[N + slot];
             if (dthc) v -= pd_thermal_at(dthc, A.Ns, N2, N + slot, taus[0]);
         }
         rhs[r] = v;
@@ -174,13 +204,19 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
 
     for (int l = 0; l < L; ++l) {
         const bool last = (l == L - 1);
-        const double* E = Eall + (long)l * N;  // E[c]: layer l, E[N + c]: layer l + 1
-        if (lane * 16 < 2 * N * N) {  // G two stages ahead into L1, six stages ahead into L2; the beam vector next to it
-            if (l + 2 < L) asm volatile("prefetch.global.L1 [%0];" ::"l"(Gc + ((long)(l + 2) * 2) * N * N + lane * 16));
-            if (l + 6 < L) asm volatile("prefetch.global.L2 [%0];" ::"l"(Gc + ((long)(l + 6) * 2) * N * N + lane * 16));
-        } else if (Bc && lane == 31 && l + 3 < L) {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(Bc + (long)(l + 3) * N2));
+        // layers l and l+1 are in the ring (staged during the previous stages); layer l+2 starts its way in now and
+        // has the whole elimination of this stage to arrive; farther layers are pulled from HBM into L2
+        if (l > 0) {
+            pd_cp_async_wait_all();
+            __syncwarp();
         }
+        if (l + 2 < L) stage_layer(l + 2);
+        if (l + 6 < L && lane * 16 < F::GL)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Gc + (long)(l + 6) * F::GL + lane * 16));
+        const double* E = ering + (l % F::RING) * N;         // exp(-k dtau*) of layer l
+        const double* E1 = ering + ((l + 1) % F::RING) * N;  // ... of layer l + 1
+        const double* Bl = bring + (l % F::RING) * N2;       // beam particular solution of layer l
+        const double* Bl1 = bring + ((l + 1) % F::RING) * N2;
 
         // ---- carry rows shift by 2N columns; freed slots load the new rows ----
         pd_static_for<0, RT>([&](auto RI) {
@@ -211,7 +247,7 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
                             v.x = -v.x;
                             v.y = -v.y;
                         } else if (nb == 3) {
-                            const pd_d2 e = *reinterpret_cast<const pd_d2*>(E + N + cc0);
+                            const pd_d2 e = *reinterpret_cast<const pd_d2*>(E1 + cc0);
                             v.x *= -e.x;
                             v.y *= -e.y;
                         }
@@ -255,7 +291,7 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
                 const int idx = pd_popc(freem & below(slot));
                 double v = 0.0;
                 if (!last) {
-                    if (beam) v = (Bc[(l + 1) * N2 + idx] - Bc[l * N2 + idx]) * att[l + 1];
+                    if (beam) v = (Bl1[idx] - Bl[idx]) * att[l + 1];
                     if (dthc)
                         v += pd_thermal_at(dthc + (long)(l + 1) * A.Ns * N2, A.Ns, N2, idx, taus[l + 1]) -
                              pd_thermal_at(dthc + (long)l * A.Ns * N2, A.Ns, N2, idx, taus[l + 1]);
@@ -268,11 +304,11 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
                             for (int j = 0; j < N; ++j) v = fma(R[idx * N + j], pd_thermal_at(dl, A.Ns, N2, N + j, taus[L]), v);
                     }
                     if (beam) {
-                        double s = -Bc[l * N2 + idx];
+                        double s = -Bl[idx];
                         if (has_bdrf) {
                             const double* q0 = A.bdrf_q0 + ((A.bdrf_percol ? (long)b * A.NBDRF : 0) + m) * N;
                             s += (mu0 * I0 / PD_PI) * q0[idx];
-                            for (int j = 0; j < N; ++j) s = fma(R[idx * N + j], Bc[l * N2 + N + j], s);
+                            for (int j = 0; j < N; ++j) s = fma(R[idx * N + j], Bl[N + j], s);
                         }
                         v = fma(s, att[L], v);
                     }
@@ -492,8 +528,13 @@ __device__ void pd_stage_b_mma(const PdStageB& A, int b, int m, double* sm, doub
                     mrow[u][cc + 3] = v4[3];
                 }
                 zj[u] = (hh == 0) ? hist[(long)l * F::HIST_PER_LAYER + N2 * N2 + jr] : 0.0;
-                if (l - 2 * PF >= 0)  // the chunk after next: from HBM into L2
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(h - 2L * PF * F::HIST_PER_LAYER));
+                // the history was written a whole forward sweep ago and has left L2 (the slots of one wave hold ~300 MB):
+                // pull the block of the layer PD_MMA_PFD steps ahead from HBM into L2, one 128-byte line per lane
+                if (l - PD_MMA_PFD >= 0) {
+                    const char* pf = reinterpret_cast<const char*>(hist + (long)(l - PD_MMA_PFD) * F::HIST_PER_LAYER);
+                    for (int ln = lane * 128; ln < (int)F::HIST_PER_LAYER * 8; ln += 32 * 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + ln));
+                }
             }
         }
 #pragma unroll
