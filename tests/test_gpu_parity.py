@@ -133,6 +133,24 @@ def test_every_kernel_variant_meets_the_same_bar(monkeypatch, env, name):
         parity_suite.check_ensemble_vs_golden(pd.pydisort, name)
 
 
+@pytest.mark.parametrize("name,ncol,first", [("sw", 4096, 20000), ("ha", 96, 500), ("lw", 8192, 100000)])
+def test_production_kernels_agree_with_the_generic_ones_on_large_slices(monkeypatch, name, ncol, first):
+    """Thousands of columns the oracle would take minutes for: the specialised kernels (symmetric stage A, tensor-core /
+    register stage B, tabulated NT) against the size-generic ones (Hessenberg-QR, shared-memory panel with Gaussian
+    elimination + triangular solves, per-output recurrences).  Two independent implementations of the same equations,
+    different pivot bookkeeping and summation orders: they must agree within the parity bar on every column (typical
+    agreement is 1e-13; columns where 1/mu0 falls next to an eigenvalue k of a layer are conditioned like
+    1/(1/mu0^2 - k^2) and move by ~1e-10 between ANY two implementations, the oracle included)."""
+    ens = synthetic.make(name, ncol, first)
+    got = parity_suite.run_batched(pd.pydisort, ens)
+    for k, v in {"PD_STAGE_B_GENERIC": "1", "PD_STAGE_A_GENERAL": "1", "PD_NT_RECURRENCE": "1"}.items():
+        monkeypatch.setenv(k, v)
+    ref = parity_suite.run_batched(pd.pydisort, ens)
+    tol = golden_io.conditioning_tolerance(ens["args"][1], 1e-9)
+    worst, _, _ = parity_suite.compare_fields(got, ref, ncol, tol, name + " production vs generic kernels")
+    assert worst < tol
+
+
 def test_unphysical_phase_function_is_flagged_not_crashed():
     """Moments that make the reduced matrices indefinite: the symmetric path must hand the item to the general
     solver, which reports the non-positive k^2 (the reference returns NaN / complex garbage here)."""
