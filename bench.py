@@ -228,6 +228,8 @@ def run_gpu(args):
     # not achieve this: their kernels interleave and both reach the copy phase at the same time -- tools/e2e_overlap.py.)
     h2d_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     host_out = {}  # (slot, name) -> pinned buffer, slot = chunk parity
+    d2h_done = {}  # running chunk number -> event of its device->host copies (buffers are reused every other chunk)
+    chunk_no = [0]
 
     def to_device_async(x, cur):
         if not isinstance(x, torch.Tensor):
@@ -240,7 +242,7 @@ def run_gpu(args):
         cur = torch.cuda.current_stream(dev)
         starts = list(range(0, B, chunk))
         h2d = d2h = 0
-        staged, done = {}, {}
+        staged = {}
 
         def stage(i):
             lo, hi = starts[i], min(B, starts[i] + chunk)
@@ -273,12 +275,14 @@ def run_gpu(args):
                 res["u"] = out[4](te, phi_dev)
             evc = torch.cuda.Event()
             evc.record(cur)
-            if i - 2 in done:  # the pinned buffers of this parity are free once their previous copy has landed
-                done.pop(i - 2).synchronize()
+            g = chunk_no[0]
+            chunk_no[0] += 1
+            if g - 2 in d2h_done:  # the pinned buffers of this parity are free once their previous copy has landed
+                d2h_done.pop(g - 2).synchronize()
             with torch.cuda.stream(d2h_stream):
                 d2h_stream.wait_event(evc)
                 for name, t in res.items():
-                    key = (i % 2, name)
+                    key = (g % 2, name)
                     if key not in host_out or host_out[key].shape != t.shape:
                         host_out[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
                     t.record_stream(d2h_stream)
@@ -286,9 +290,10 @@ def run_gpu(args):
                     d2h += t.numel() * 8
                 evd = torch.cuda.Event()
                 evd.record(d2h_stream)
-            done[i] = evd
+            d2h_done[g] = evd
             del out, res
-        cur.wait_stream(d2h_stream)
+        # no wait here: the copies of the last chunk overlap the first chunk of the next step; `timed` closes the
+        # timed region only after the copy stream has drained
         return h2d, d2h
 
     def step(a, kw, tau_eval, to_host):
@@ -307,6 +312,7 @@ def run_gpu(args):
         extra = None
         for _ in range(nsteps):
             extra = fn()
+        torch.cuda.current_stream(dev).wait_stream(d2h_stream)  # results of the last step have reached the host
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
