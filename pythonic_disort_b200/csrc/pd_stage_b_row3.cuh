@@ -33,9 +33,11 @@ struct PdStageBRow3 {
     static constexpr int N2 = 2 * N, RC = 4 * N, NCOL = 4 * N + 1, HROW = 2 * N + 1;
     static constexpr int LDB = 4 * N + 2;   // published pivot row (even length: 128-bit accesses)
     static constexpr int SMEM_FIXED = 2 * LDB + 2 * N2 + N * N;
-    // buf[2][LDB], xs, 1/pivot of the stage, R, exp(-k dtau*)[L][N], exp(-tau*/mu0)[L+1]; the per-system stride is 2 (mod 16) doubles so that
-    // the 32/N systems of a warp read their pivot rows from disjoint 16-byte bank groups
-    PD_HD static int smem_doubles(int L) { return ((SMEM_FIXED + L * N + L + 1 + 13) / 16) * 16 + 2; }
+    // buf[2][LDB], xs, 1/pivot of the stage, R, a three-layer ring of exp(-k dtau*)[N] (computed one stage ahead, one
+    // value per lane: the full [L][N] table used to set the number of resident systems), exp(-tau*/mu0)[L+1]; the
+    // per-system stride is 2 (mod 16) doubles so that the 32/N systems of a warp read their pivot rows from disjoint
+    // 16-byte bank groups
+    PD_HD static int smem_doubles(int L) { return ((SMEM_FIXED + 3 * N + L + 1 + 13) / 16) * 16 + 2; }
     static constexpr long HIST_PER_LAYER = (long)N2 * HROW;
 };
 
@@ -56,8 +58,8 @@ __device__ void pd_stage_b_row3(const SubWarp<N>& g, const PdStageB& A, int b, i
     double* xs = buf + 2 * F::LDB;       // [2N]
     double* pinvs = xs + N2;             // [2N] 1/pivot of every step of the current stage
     double* R = pinvs + N2;              // [N][N]
-    double* Eall = R + N * N;            // [L][N]  exp(-k_l dtau*_l)
-    double* att = Eall + (long)L * N;    // [L+1]   exp(-tau*_l / mu0)
+    double* Er = R + N * N;              // [3][N]  exp(-k_l dtau*_l) of layers l, l+1 (in use) and l+2 (being computed)
+    double* att = Er + 3 * N;            // [L+1]   exp(-tau*_l / mu0)
 
     const long sys = (long)b * A.NF + m;
     const double* taus = A.taus + (long)b * (L + 1);
@@ -86,10 +88,11 @@ __device__ void pd_stage_b_row3(const SubWarp<N>& g, const PdStageB& A, int b, i
         for (int idx = lane; idx < N * N; idx += LPS)
             R[idx] = ((m == 0) ? 2.0 : 1.0) * q[idx] * A.mu[idx % N] * A.w[idx % N];
     }
-    for (int idx = lane; idx < L * N; idx += LPS) {
-        const int ll = idx / N;
-        Eall[idx] = exp(-Kc[idx] * (taus[ll + 1] - taus[ll]));
-    }
+    auto stage_E = [&](int ll) {  // LPS == N: one value per lane
+        Er[(ll % 3) * N + lane] = exp(-Kc[(long)ll * N + lane] * (taus[ll + 1] - taus[ll]));
+    };
+    stage_E(0);
+    if (L > 1) stage_E(1);
     if (beam)
         for (int ll = lane; ll <= L; ll += LPS) att[ll] = exp(-taus[ll] / mu0);
     __syncwarp();
@@ -113,7 +116,7 @@ __device__ void pd_stage_b_row3(const SubWarp<N>& g, const PdStageB& A, int b, i
 #pragma unroll
         for (int c = 0; c < N; ++c) {
             a[0][c] = g0[c];
-            a[0][N + c] = g1[c] * Eall[c];
+            a[0][N + c] = g1[c] * Er[c];
         }
         double v = have_b ? bneg[lane] : 0.0;
         if (beam) v -= Bc[r];
@@ -124,7 +127,9 @@ __device__ void pd_stage_b_row3(const SubWarp<N>& g, const PdStageB& A, int b, i
 
     for (int l = 0; l < L; ++l) {
         const bool last = (l == L - 1);
-        const double* E = Eall + (long)l * N;  // E[c]: layer l, E[N + c]: layer l + 1
+        const double* E = Er + (l % 3) * N;          // E[c]: layer l
+        const double* E1 = Er + ((l + 1) % 3) * N;   // E1[c]: layer l + 1
+        if (l + 2 < L) stage_E(l + 2);  // read two stages from now; its slot was last read in stage l - 1
         if (l + 2 < L && lane * 16 < 2 * N * N)
             asm volatile("prefetch.global.L1 [%0];" ::"l"(Gc + ((long)(l + 2) * 2) * N * N + lane * 16));
 
@@ -161,8 +166,8 @@ __device__ void pd_stage_b_row3(const SubWarp<N>& g, const PdStageB& A, int b, i
                         a[r][N + c + 1] = v1.y;
                         a[r][N2 + c] = -w0.x;
                         a[r][N2 + c + 1] = -w0.y;
-                        a[r][3 * N + c] = -w1.x * E[N + c];
-                        a[r][3 * N + c + 1] = -w1.y * E[N + c + 1];
+                        a[r][3 * N + c] = -w1.x * E1[c];
+                        a[r][3 * N + c + 1] = -w1.y * E1[c + 1];
                     }
                     double v = 0.0;
                     if (beam) v = (Bc[(l + 1) * N2 + idx] - Bc[l * N2 + idx]) * att[l + 1];
