@@ -166,8 +166,11 @@ static bool use_r3(int N) {
     return true;
 }
 
+#ifndef PD_R3_MINB4
+#define PD_R3_MINB4 5  // resident CTAs (of two warps) per SM the N = 4 register kernel is compiled for
+#endif
 template <int N>
-__global__ void __launch_bounds__(64, (N == 8) ? 4 : 6) k_stage_b_r3(PdStageB a, double* hist, long hist_doubles) {
+__global__ void __launch_bounds__(64, (N == 8) ? 4 : PD_R3_MINB4) k_stage_b_r3(PdStageB a, double* hist, long hist_doubles) {
     extern __shared__ double smem[];
     const int SD = PdStageBRow3<N>::smem_doubles(a.L);
     constexpr int GPW = 32 / N;  // systems per warp
