@@ -5,32 +5,42 @@
 #include "pd_stage_a_sym.cuh"
 
 template <int LANES, int NC>
-__global__ void k_stage_a(PdStageA a, const double* __restrict__ ptab, int items_per_cta, int item_doubles) {
+__global__ void k_stage_a(PdStageA a, const double* __restrict__ ptab, int items_per_cta, int item_doubles, int reps) {
     extern __shared__ double smem[];
     const int m = blockIdx.y;
     const int n = NC > 0 ? NC : a.N, nm = a.NLeg - m;
-    if (a.only_flagged) {  // fallback pass after the symmetric kernel: leave at once unless an item of this CTA is flagged
-        const int gi0 = threadIdx.x / LANES;
-        const long it0 = (long)blockIdx.x * items_per_cta + gi0;
-        bool flagged = false;
-        if (gi0 < items_per_cta && it0 < (long)a.B * a.L && (threadIdx.x % LANES) == 0) {
-            const double k0 = a.K[(((it0 / a.L) * a.NF + m) * a.L + it0 % a.L) * n];
-            flagged = !(k0 == k0);
-        }
-        if (!__syncthreads_or(flagged)) return;
-    }
-    double* Q = smem;  // [nm][n] scaled Legendre table of this mode
-    for (int idx = threadIdx.x; idx < nm * n; idx += blockDim.x) {
-        const int i = idx % n;
-        Q[idx] = ptab[((long)m * a.NLeg + m) * n + idx] * sqrt(a.w[i] / a.mu[i]);
-    }
-    __syncthreads();
+    double* Q = smem;  // [nm][n] scaled Legendre table of this mode (built when the CTA has work)
     const int gi = threadIdx.x / LANES;
-    const long it = (long)blockIdx.x * items_per_cta + gi;
-    if (gi >= items_per_cta || it >= (long)a.B * a.L) return;
-    SubWarp<LANES> g;
-    double* sm = smem + ((nm * n + 1) & ~1) + (long)gi * item_doubles;
-    pd_stage_a_item<SubWarp<LANES>, NC>(g, a, (int)(it / a.L), m, (int)(it % a.L), Q, sm);
+    const long items = (long)a.B * a.L;
+    bool have_q = false;
+    // reps = 1 in the normal pass.  The fallback pass after the symmetric kernel (only_flagged) gives every CTA
+    // `reps` consecutive item groups and skips a group unless one of its items is flagged: almost always none is,
+    // and a million CTAs that only look at one flag each cost more than the looking (1.5 ms per 16k SW columns).
+    for (int r = 0; r < reps; ++r) {
+        const long it = ((long)blockIdx.x * reps + r) * items_per_cta + gi;
+        const bool valid = gi < items_per_cta && it < items;
+        if (a.only_flagged) {
+            bool flagged = false;
+            if (valid && (threadIdx.x % LANES) == 0) {
+                const double k0 = a.K[(((it / a.L) * a.NF + m) * a.L + it % a.L) * n];
+                flagged = !(k0 == k0);
+            }
+            if (!__syncthreads_or(flagged)) continue;
+        }
+        if (!have_q) {
+            for (int idx = threadIdx.x; idx < nm * n; idx += blockDim.x) {
+                const int i = idx % n;
+                Q[idx] = ptab[((long)m * a.NLeg + m) * n + idx] * sqrt(a.w[i] / a.mu[i]);
+            }
+            __syncthreads();
+            have_q = true;
+        }
+        if (valid) {
+            SubWarp<LANES> g;
+            double* sm = smem + ((nm * n + 1) & ~1) + (long)gi * item_doubles;
+            pd_stage_a_item<SubWarp<LANES>, NC>(g, a, (int)(it / a.L), m, (int)(it % a.L), Q, sm);
+        }
+    }
 }
 
 // one thread per item, symmetric (Cholesky + Jacobi) path, N = 4 or 8
@@ -106,11 +116,12 @@ int pd_launch_stage_a(const PdStageA& a_in, const double* ptab, cudaStream_t st)
     const size_t smem = qbytes + (size_t)ipc * item_doubles * 8;
     if (smem > PD_SMEM_MAX_CTA) return -22;
     const long items = (long)a.B * a.L;
-    dim3 grid((unsigned)((items + ipc - 1) / ipc), a.NF);
+    const int reps = a.only_flagged ? 16 : 1;
+    dim3 grid((unsigned)((items + (long)ipc * reps - 1) / ((long)ipc * reps)), a.NF);
     cudaError_t e = cudaSuccess;
     PD_DISPATCH_N(N, {
         e = cudaFuncSetAttribute(k_stage_a<LN, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) k_stage_a<LN, NC><<<grid, threads, smem, st>>>(a, ptab, ipc, item_doubles);
+        if (e == cudaSuccess) k_stage_a<LN, NC><<<grid, threads, smem, st>>>(a, ptab, ipc, item_doubles, reps);
     });
     if (e != cudaSuccess) return (int)e;
     return (int)cudaGetLastError();
