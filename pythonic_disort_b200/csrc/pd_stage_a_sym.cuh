@@ -56,8 +56,12 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
     const bool thermal = a.iso && m == 0;
     const bool beam = a.beam && a.colp[(long)b * PD_NCOLP + PD_COL_I0] > 0.0;
 
-    bool active = false;  // _solve_for_gen_and_part_sols.py:119
-    for (int t = 0; t < nm; ++t) active = active || (fabs((omega / 2) * wl[t]) > 1e-8);
+    // the beam coefficients of this (column, mode) are read in the assembly loop below: start that miss now
+#if defined(__CUDA_ARCH__)
+    if (beam) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pmu0 + ((long)b * a.NF + m) * a.NLeg + m));
+#endif
+    bool active = false;  // _solve_for_gen_and_part_sols.py:119  (no short circuit: the loads go out back to back)
+    for (int t = 0; t < nm; ++t) active |= (fabs((omega / 2) * wl[t]) > 1e-8);
     if (!active) {  // shortcut (:162-168): G = [[0, I], [I, 0]], K = 1/mu, B = 0
         double* Kout = a.K + item * N;
         double* Gp_out = a.G + item * 2 * N * N;

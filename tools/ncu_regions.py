@@ -1,5 +1,6 @@
 import sys,re
 reg=eval(sys.argv[1])
+fname=sys.argv[2] if len(sys.argv)>2 else 'pd_stage_b_mma.cuh'
 acc={r[0]:[0,0] for r in reg}; other=[0,0]
 for ln in sys.stdin:
     m=re.match(r'\s*([\d.]+)% inst\s+([\d.]+)% stall\s+(\S+):(\d+)',ln)
@@ -7,7 +8,7 @@ for ln in sys.stdin:
         if ln.startswith('total'): print(ln.strip())
         continue
     i,s,f,l=float(m[1]),float(m[2]),m[3],int(m[4])
-    if f!='pd_stage_b_mma.cuh':
+    if f!=fname:
         other[0]+=i; other[1]+=s
         if s>1.5: print('other',ln.strip()[:110])
         continue
