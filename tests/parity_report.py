@@ -1,13 +1,13 @@
 #!/usr/bin/env python
-"""Parity table for profiles/: the CUDA path (through the public API / C ABI) against the oracle on seeded ensemble
+"""Test infrastructure (it runs the oracle): parity table for profiles/: the CUDA path (through the public API / C ABI) against the oracle on seeded ensemble
 slices, per output field: worst  max|X - X_ref| / max|X_ref|  over the columns (the SURVEY 8(c) metric)."""
 import multiprocessing as mp
 import os
 import sys
 import warnings
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))                   # tests/ (golden_io, parity_suite)
 for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
     os.environ.setdefault(_v, "1")
 import numpy as np  # noqa: E402
