@@ -44,9 +44,11 @@ __global__ void k_stage_a(PdStageA a, const double* __restrict__ ptab, int items
 }
 
 // one thread per item, symmetric (Cholesky + Jacobi) path, N = 4 or 8
+#ifndef PD_SYM_THREADS
 #define PD_SYM_THREADS 128
+#endif
 template <int N>
-__global__ void __launch_bounds__(PD_SYM_THREADS, (N <= 4) ? 4 : 2) k_stage_a_sym(PdStageA a, const double* __restrict__ ptab) {
+__global__ void __launch_bounds__(PD_SYM_THREADS, ((N <= 4) ? 4 : 2) * (128 / PD_SYM_THREADS)) k_stage_a_sym(PdStageA a, const double* __restrict__ ptab) {
     extern __shared__ double smem[];
     using P = PdSym<N>;
     const int m = blockIdx.y, nm = a.NLeg - m;
