@@ -195,6 +195,17 @@ int pd_planck_band(long n, const double* T, double wvnmlo, double wvnmhi, const 
 int pd_s_poly_coeffs(int B, int L, const double* tau, const double* temper, double wvnmlo, double wvnmhi,
                      const double* gl16, double* s_poly, void* stream);
 
+/* Surface input on the device: Fourier modes m < NF of the Hapke BDRF of DISORT's test problems
+ * (pydisotest/6_test.py:11-24) in the relative azimuth, as the reference's users compute them with quad_vec
+ * (pydisotest/6_test.py:193-201) before handing them to pydisort() / cache_BDRF_Fourier_modes (subroutines.py:490-570):
+ *   out[m][i][j] = 1 / ((1 + delta_m0) pi) * int_0^2pi Hapke(mu[i], mup[j], dphi) cos(m dphi) d dphi,   i < N, j < M,
+ * as 2 int_0^pi by npanel 16-point Gauss-Legendre panels (gl16[32]: nodes on [-1, 1], then weights; the integrand is even
+ * about pi and analytic on [0, pi], also on the diagonal mu == mu' where the opposition surge has its cusp at pi).
+ * mup = the quadrature nodes gives q^m(mu_i, mu_j); mup = the beam cosines of B columns gives the per-column
+ * q^m(mu_i, mu0_b).  NF <= 64, 16 npanel >= NF. */
+int pd_hapke_modes(int N, long M, int NF, int npanel, const double* gl16, const double* mu, const double* mup, double B0,
+                   double HH, double W, double* out, void* stream);
+
 /* FP64 FMA throughput probe (one launch of dependent-free DFMA chains); used
  * by bench.py to measure the FP64 roofline denominator on the box.
  * Returns the number of FLOPs the launch performs; time it with CUDA events. */

@@ -40,7 +40,7 @@ CHK = dict(TAU_POS=1 << 0, THICK_POS=1 << 1, OMEGA_RANGE=1 << 2, LEG_RANGE=1 << 
            MU0_AT_NODE=1 << 11)
 
 EXPORTS = ["pd_abi_version", "pd_workspace_bytes", "pd_prologue", "pd_solve", "pd_solve_stages", "pd_eval_flux", "pd_eval_u0",
-           "pd_eval_u", "pd_interp_mu", "pd_planck_band", "pd_s_poly_coeffs", "pd_fp64_probe"]
+           "pd_eval_u", "pd_interp_mu", "pd_planck_band", "pd_s_poly_coeffs", "pd_hapke_modes", "pd_fp64_probe"]
 
 
 def needs_build():
@@ -102,6 +102,8 @@ def bind(path):
     lib.pd_planck_band.argtypes = [ctypes.c_long, vp, ctypes.c_double, ctypes.c_double, vp, vp, vp]
     lib.pd_s_poly_coeffs.restype = ci
     lib.pd_s_poly_coeffs.argtypes = [ci, ci, vp, vp, ctypes.c_double, ctypes.c_double, vp, vp, vp]
+    lib.pd_hapke_modes.restype = ci
+    lib.pd_hapke_modes.argtypes = [ci, ctypes.c_long, ci, ci, vp, vp, vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, vp, vp]
     lib.pd_fp64_probe.restype = ctypes.c_double
     lib.pd_fp64_probe.argtypes = [vp, ci, vp]
     if lib.pd_abi_version() != 1:

@@ -275,6 +275,21 @@ def s_poly_coeffs(tau_arr, TEMPER, WVNMLO, WVNMHI):
     return out[0] if single else out
 
 
+def hapke_modes(N, NF, mup, B0, HH, W, n_panels):
+    """Fourier modes of the Hapke BDRF on the device (row f4): ``mup`` is a 1-D tensor of incidence cosines (the
+    quadrature nodes, or one beam cosine per column); returns a tensor ``[NF, N, len(mup)]``."""
+    from .subroutines import Gauss_Legendre_quad
+    lib, dev = _backend()
+    mu = torch.as_tensor(Gauss_Legendre_quad(N)[0], dtype=_F64, device=dev)
+    mp = mup.to(device=dev, dtype=_F64).contiguous().reshape(-1)
+    out = torch.empty((NF, N, mp.numel()), dtype=_F64, device=dev)
+    rc = lib.pd_hapke_modes(N, mp.numel(), NF, int(n_panels), _ptr(_gl16(dev)), _ptr(mu), _ptr(mp), float(B0), float(HH),
+                            float(W), _ptr(out), _stream(dev))
+    if rc != 0:
+        raise RuntimeError(f"libpydisort_b200: pd_hapke_modes failed with code {rc}")
+    return out
+
+
 def barycentric_weight_matrix(mu, N):
     """Weight matrix [nmu, 2N] of ``subroutines.interpolate`` (subroutines.py:614-705): row o holds the barycentric
     Lagrange weights of the N Gauss-Legendre streams of the hemisphere of ``mu[o]`` (``mu > 0``: the upward streams

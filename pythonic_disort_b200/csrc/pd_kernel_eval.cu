@@ -321,7 +321,33 @@ __global__ void k_s_poly_coeffs(int L, const double* __restrict__ tau, const dou
     }
 }
 
+// Hapke BDRF Fourier modes (row f4): one thread per (reflection node i, incidence cosine j); out[m][i][j]
+template <int NFMAX>
+__global__ void k_hapke_modes(int N, long M, int NF, int npanel, const double* __restrict__ gl, const double* __restrict__ mu,
+                              const double* __restrict__ mup, double B0, double HH, double W, double* __restrict__ out) {
+    __shared__ double g[32];
+    if (threadIdx.x < 32) g[threadIdx.x] = gl[threadIdx.x];
+    __syncthreads();
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)N * M) return;
+    const int i = (int)(idx / M);
+    const long j = idx - (long)i * M;
+    pd_hapke_modes_point<NFMAX>(mu[i], mup[j], NF, npanel, g, B0, HH, W, out + (long)i * M + j, (long)N * M);
+}
+
 extern "C" {
+
+int pd_hapke_modes(int N, long M, int NF, int npanel, const double* gl16, const double* mu, const double* mup, double B0,
+                   double HH, double W, double* out, void* stream) {
+    if (N < 1 || M < 1 || NF < 1 || NF > 64 || npanel < 1 || 16 * npanel < NF || !gl16 || !mu || !mup || !out) return -60;
+    const int threads = 128;
+    const long blocks = ((long)N * M + threads - 1) / threads;
+    if (blocks > 2147483647L) return -61;
+    if (NF <= 16) k_hapke_modes<16><<<(unsigned)blocks, threads, 0, pd_stream(stream)>>>(N, M, NF, npanel, gl16, mu, mup, B0, HH, W, out);
+    else if (NF <= 32) k_hapke_modes<32><<<(unsigned)blocks, threads, 0, pd_stream(stream)>>>(N, M, NF, npanel, gl16, mu, mup, B0, HH, W, out);
+    else k_hapke_modes<64><<<(unsigned)blocks, threads, 0, pd_stream(stream)>>>(N, M, NF, npanel, gl16, mu, mup, B0, HH, W, out);
+    return (int)cudaGetLastError();
+}
 
 int pd_planck_band(long n, const double* T, double wvnmlo, double wvnmhi, const double* gl16, double* out, void* stream) {
     if (n < 1 || !T || !gl16 || !out) return -50;

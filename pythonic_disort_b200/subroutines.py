@@ -20,7 +20,7 @@ __all__ = [
     "Clenshaw_Curtis_quad", "atleast_2d_append", "generate_diff_act_flux_funcs", "Planck",
     "blackbody_contrib_to_BCs", "linear_spline_coefficients", "generate_s_poly_coeffs",
     "generate_emissivity_from_BDRF", "cache_BDRF_Fourier_modes", "affine_transform_poly_coeffs",
-    "interpolate", "TabulatedBDRF",
+    "interpolate", "TabulatedBDRF", "hapke_BDRF_Fourier_modes",
 ]
 
 
@@ -215,8 +215,12 @@ class TabulatedBDRF:
     ``pydisort`` recognises instances and uses the tables directly."""
 
     def __init__(self, q, q0=None):
-        self.q = np.asarray(q, dtype=float)
-        self.q0 = None if q0 is None else np.asarray(q0, dtype=float).reshape(self.q.shape[0], -1)
+        if _is_tensor(q):  # device tables (e.g. from hapke_BDRF_Fourier_modes): kept as they are
+            self.q = q
+            self.q0 = None if q0 is None else q0.reshape(q.shape[0], -1)
+        else:
+            self.q = np.asarray(q, dtype=float)
+            self.q0 = None if q0 is None else np.asarray(q0, dtype=float).reshape(self.q.shape[0], -1)
         self.nodes = Gauss_Legendre_quad(self.q.shape[0])[0]
 
     def __call__(self, mu, neg_mup):
@@ -226,6 +230,21 @@ class TabulatedBDRF:
         if self.q0 is None:
             raise ValueError("this BDRF mode was tabulated without a beam direction")
         return self.q0
+
+
+def hapke_BDRF_Fourier_modes(N, NFourier, mu0, B0=1.0, HH=0.06, W=0.6, n_panels=64):
+    """The first ``NFourier`` Fourier modes of the Hapke surface BDRF of DISORT's test problems
+    (pydisotest/6_test.py:11-24), tabulated at the ``N`` quadrature nodes and at the beam cosine(s) ``mu0`` -- what a
+    user of the reference builds with ``quad_vec`` over the relative azimuth (pydisotest/6_test.py:193-201) and then
+    passes to ``pydisort`` / ``cache_BDRF_Fourier_modes``.  Here the integration runs on the GPU (``pd_hapke_modes``:
+    ``n_panels`` 16-point Gauss-Legendre panels on [0, pi], where the integrand is analytic) and ``mu0`` may hold one value per column: the returned list of
+    ``TabulatedBDRF`` (device tables) is a valid ``BDRF_Fourier_modes`` argument for a batched ``pydisort`` call."""
+    import torch
+    from . import api
+    mu0_t = torch.atleast_1d(torch.as_tensor(mu0, dtype=torch.float64))
+    nodes = torch.as_tensor(Gauss_Legendre_quad(N)[0], dtype=torch.float64)
+    tab = api.hapke_modes(N, NFourier, torch.cat([nodes, mu0_t.reshape(-1).cpu()]), B0, HH, W, n_panels)  # [NF, N, N + k]
+    return [TabulatedBDRF(tab[m, :, :N], tab[m, :, N:]) for m in range(NFourier)]
 
 
 def cache_BDRF_Fourier_modes(N, BDRF_Fourier_modes, mu0=0):

@@ -14,6 +14,8 @@ What it does
      quadrature nodes (that is all the solver ever asks of them);
   2. copies the Stamnes DISORT 4.0.99 result files the tests compare against
      (data, not code) to ``tests/golden/stamnes/``;
+  6. (``hapke``) builds the Fourier modes of the Hapke BDRF the way the reference's test problem 6b does (quad_vec over the
+     relative azimuth, here with a tight tolerance) -> ``tests/golden/hapke_modes.npz``;
   5. (``thermal``) runs the reference's ``blackbody_contrib_to_BCs`` / ``generate_s_poly_coeffs`` on fixed temperatures,
      bands and atmospheres -> ``tests/golden/thermal_inputs.npz``;
   4. (``interpolate``) runs the reference's ``subroutines.interpolate`` on its own ``u`` / ``u0`` at the user
@@ -263,8 +265,27 @@ def run_thermal():
     print("thermal inputs:", em.shape, sp.shape)
 
 
+def run_hapke():
+    """Row f4: Fourier modes of the Hapke BDRF exactly as the reference's test problem 6b builds them
+    (pydisotest/6_test.py:11-24 and :193-201: quad_vec over the relative azimuth), at the quadrature nodes and at two
+    beam cosines."""
+    spec = importlib.util.spec_from_file_location("ref_test6", os.path.join(REF, "pydisotest", "6_test.py"))
+    t6 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(t6)
+    N, NF = 8, 10
+    B0, HH, W = 1, 0.06, 0.6
+    mu = ref_sub.Gauss_Legendre_quad(N)[0]
+    cols = np.concatenate([mu, [0.5, 0.3137]])
+    import scipy.integrate
+    modes = np.array([scipy.integrate.quad_vec(lambda dphi: t6.Hapke(mu, cols, dphi, B0, HH, W) * np.cos(m * dphi), 0, 2 * np.pi,
+                                               epsrel=1e-12, limit=4000)[0] / ((1 + (m == 0)) * np.pi) for m in range(NF)])
+    np.savez_compressed(os.path.join(HERE, "hapke_modes.npz"), N=np.array(N), mu0=cols[N:], params=np.array([B0, HH, W]),
+                        modes=modes)
+    print("hapke modes:", modes.shape)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["suite", "stamnes", "ensembles", "interpolate", "thermal"]
+    what = sys.argv[1:] or ["suite", "stamnes", "ensembles", "interpolate", "thermal", "hapke"]
     if "suite" in what:
         run_reference_suite()
     if "stamnes" in what:
@@ -275,3 +296,5 @@ if __name__ == "__main__":
         run_interpolate()
     if "thermal" in what:
         run_thermal()
+    if "hapke" in what:
+        run_hapke()

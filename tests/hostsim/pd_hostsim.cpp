@@ -218,6 +218,15 @@ int pd_s_poly_coeffs(int B, int L, const double* tau, const double* temper, doub
     return 0;
 }
 
+int pd_hapke_modes(int N, long M, int NF, int npanel, const double* gl16, const double* mu, const double* mup, double B0,
+                   double HH, double W, double* out, void*) {
+    if (N < 1 || M < 1 || NF < 1 || NF > 64 || npanel < 1 || 16 * npanel < NF || !gl16 || !mu || !mup || !out) return -60;
+    for (int i = 0; i < N; ++i)
+        for (long j = 0; j < M; ++j)
+            pd_hapke_modes_point<64>(mu[i], mup[j], NF, npanel, gl16, B0, HH, W, out + (long)i * M + j, (long)N * M);
+    return 0;
+}
+
 double pd_fp64_probe(double*, int, void*) { return -1.0; }
 
 }  // extern "C"

@@ -152,3 +152,20 @@ def check_thermal_inputs_vs_golden(pd_module, tol=1e-9):
         host = sub.generate_s_poly_coeffs(gold["tau"], gold["temper"], lo, hi)  # NumPy input: host route, batched
         np.testing.assert_allclose(host, ref, rtol=1e-7, atol=1e-9 * np.max(np.abs(ref)))
     return worst
+
+
+def check_hapke_modes_vs_golden(pd_module):
+    """Row f4: Fourier modes of the Hapke BDRF on the device (pd_hapke_modes) against the quad_vec construction of the
+    reference's test problem 6b (tests/golden/hapke_modes.npz, integrated to 1e-12)."""
+    import torch
+    sub = pd_module.subroutines
+    gold = np.load(os.path.join(golden_io.GOLDEN, "hapke_modes.npz"))
+    N, ref = int(gold["N"]), gold["modes"]
+    B0, HH, W = gold["params"]
+    NF = ref.shape[0]
+    modes = sub.hapke_BDRF_Fourier_modes(N, NF, torch.as_tensor(gold["mu0"]), B0, HH, W)
+    got = np.stack([np.concatenate([to_np(fm.q), to_np(fm.q0)], axis=1) for fm in modes])
+    assert got.shape == ref.shape
+    err = np.abs(got - ref) / np.max(np.abs(ref[0]))
+    assert err.max() <= 1e-9, err.max()
+    return err.max()

@@ -68,6 +68,32 @@ def test_thermal_source_inputs_on_the_device():
     np.testing.assert_allclose(parity_suite.to_np(a), b, rtol=1e-7)
 
 
+def test_hapke_fourier_modes_on_the_device_and_per_column_beam_directions():
+    """Row f4 (pydisotest/6_test.py:11-24, :193-201): pd_hapke_modes against the reference-style quad_vec tables, and
+    the per-column use: every column its own mu0, one batched call with per-column tables against column-by-column
+    calls with that column's tables."""
+    import torch
+    parity_suite.check_hapke_modes_vs_golden(pd)
+    B, L, NQuad = 6, 3, 16
+    rng = np.random.default_rng(7)
+    tau = np.cumsum(rng.uniform(0.1, 0.6, (B, L)), axis=1)
+    omega = rng.uniform(0.2, 0.9, (B, L))
+    Leg = (rng.uniform(0.3, 0.7, (B, L))[:, :, None]) ** np.arange(NQuad + 1)[None, None, :]
+    mu0 = rng.uniform(0.25, 0.95, B)
+    modes = pd.subroutines.hapke_BDRF_Fourier_modes(NQuad // 2, NQuad, torch.as_tensor(mu0))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = pd.pydisort(tau, omega, NQuad, Leg, mu0, np.full(B, 3.0), 0.0, BDRF_Fourier_modes=modes)
+        Fp = out[1](tau)
+        for b in range(B):
+            mine = pd.subroutines.hapke_BDRF_Fourier_modes(NQuad // 2, NQuad, float(mu0[b]))
+            one = pd.pydisort(tau[b], omega[b], NQuad, Leg[b], mu0[b], 3.0, 0.0, BDRF_Fourier_modes=mine)
+            np.testing.assert_allclose(Fp[b], one[1](tau[b]), rtol=1e-12)
+            trap = synthetic.hapke_fourier_tables(NQuad // 2, NQuad, mu0[b], n_phi=8192)  # independent rule, 1/n^2 on the diagonal
+            two = pd.pydisort(tau[b], omega[b], NQuad, Leg[b], mu0[b], 3.0, 0.0, BDRF_Fourier_modes=trap)
+            np.testing.assert_allclose(Fp[b], two[1](tau[b]), rtol=1e-6)
+
+
 @pytest.mark.parametrize("name,ncol,first", [("sw", 48, 1000), ("lw", 256, 5000), ("tp1", 6, 0), ("tp9c", 2, 0)])
 def test_ensembles_vs_live_oracle(name, ncol, first):
     from oracle import disort_oracle

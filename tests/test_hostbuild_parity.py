@@ -44,6 +44,10 @@ def test_thermal_source_inputs():
     parity_suite.check_thermal_inputs_vs_golden(pd)
 
 
+def test_hapke_fourier_modes():
+    parity_suite.check_hapke_modes_vs_golden(pd)
+
+
 def _counts(lib):
     import ctypes
     lib.pd_hostsim_count.restype = ctypes.c_long
