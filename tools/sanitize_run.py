@@ -4,7 +4,7 @@
     compute-sanitizer --tool memcheck  python tools/sanitize_run.py
     compute-sanitizer --tool racecheck python tools/sanitize_run.py
 
-Covers SW (N = 8: symmetric stage A, tensor-core stage B, u + tabulated NT, interpolate), LW (N = 4: three-row
+Covers the input helpers (Planck band integrals, s_poly coefficients, Hapke Fourier modes), SW (N = 8: symmetric stage A, tensor-core stage B, u + tabulated NT, interpolate), LW (N = 4: three-row
 register stage B, thermal source) and HA (N = 16: general stage A, tensor-core stage B, BDRF surface)."""
 import os
 import sys
@@ -31,4 +31,14 @@ for name, ncol in (("sw", 6), ("lw", 20), ("ha", 2)):
         chk += float(np.sum(u)) + float(np.sum(um))
     assert np.isfinite(chk), name
     print(name, "ok", chk)
+import torch  # noqa: E402
+
+T = torch.linspace(0.0, 320.0, 257, device="cuda", dtype=torch.float64)
+em = pd.subroutines.blackbody_contrib_to_BCs(T, 600.0, 700.0)
+tau = torch.cumsum(torch.rand(5, 12, device="cuda", dtype=torch.float64) + 0.1, dim=1)
+tem = torch.linspace(200.0, 300.0, 13, device="cuda", dtype=torch.float64).repeat(5, 1)
+sp = pd.subroutines.generate_s_poly_coeffs(tau, tem, 10.0, 3000.0)
+modes = pd.subroutines.hapke_BDRF_Fourier_modes(8, 16, torch.tensor([0.3, 0.6, 0.9]))
+assert bool(torch.isfinite(em).all()) and bool(torch.isfinite(sp).all()) and bool(torch.isfinite(modes[3].q0).all())
+print("input helpers ok", float(em.sum()), float(sp.sum()), float(modes[0].q.sum()))
 print("sanitizer run finished")
