@@ -405,7 +405,7 @@ def run_gpu(args):
     bytes_k = {"solve_eigen": item * (NLeg + 1) * 8 + item * (2 * N * N + N + 2 * N) * 8,
                "solve_bc": item * (2 * N * N + N + 2 * N) * 8 + item * 2 * N * 8}[dom]
     kname = {"solve_eigen": "k_stage_a_sym" if N in (4, 8) else "k_stage_a",
-             "solve_bc": "k_stage_b_mma" if N in (8, 16) else ("k_stage_b_r3" if N == 4 else "k_stage_b")}[dom]
+             "solve_bc": "k_stage_b_add" if N in (2, 4, 8, 16) else "k_stage_b"}[dom]
     # DRAM bytes per column of that kernel from the committed ncu capture (profiles/r1_traffic.json), if any
     traffic = None
     try:

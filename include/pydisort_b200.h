@@ -34,6 +34,10 @@ extern "C" {
 #define PD_FLAG_ISO       (1 << 1) /* there_is_iso_source   (pydisort.py:216)            */
 #define PD_FLAG_DELTA_M   (1 << 2) /* np.any(f_arr > 0)     (pydisort.py:316)            */
 #define PD_FLAG_BDRF_PERCOL (1 << 3) /* bdrf_q / bdrf_q0 carry a leading B axis          */
+#define PD_FLAG_GENERIC_KERNELS (1 << 8) /* TEST BIT: run the size-generic kernels (Hessenberg-QR eigen stage, pivoted
+                                          * band solver, per-output NT recurrences) where a production kernel
+                                          * specialised for this NQuad / NLeg_all exists; results agree to rounding.
+                                          * The only kernel-selection switch of the library (no environment variables). */
 
 /* per-column status bits (pd_solve) */
 #define PD_ST_QR_NOCONV   (1 << 0) /* shifted QR hit its iteration cap                   */

@@ -31,7 +31,7 @@ class pd_state(ctypes.Structure):
 
 
 # constants of include/pydisort_b200.h
-PD_FLAG_BEAM, PD_FLAG_ISO, PD_FLAG_DELTA_M, PD_FLAG_BDRF_PERCOL = 1, 2, 4, 8
+PD_FLAG_BEAM, PD_FLAG_ISO, PD_FLAG_DELTA_M, PD_FLAG_BDRF_PERCOL, PD_FLAG_GENERIC_KERNELS = 1, 2, 4, 8, 256
 PD_ST_QR_NOCONV, PD_ST_BAD_EIGEN, PD_ST_ZERO_PIVOT = 1, 2, 4
 PD_NCOLP = 8
 PD_COL_MU0, PD_COL_I0, PD_COL_RESCALE, PD_COL_PHI0, PD_COL_I0_RAW, PD_COL_DM, PD_COL_NT = 0, 1, 2, 3, 4, 5, 6

@@ -35,7 +35,6 @@ from . import _lib
 from .subroutines import Gauss_Legendre_quad, TabulatedBDRF
 
 _F64 = torch.float64
-_test_backend = None  # set by tests/hostsim only: (ctypes lib, torch.device("cpu"))
 _const_cache = {}
 _profile = None  # bench.py sets this to a list to collect (label, CUDA event) marks around each launch
 
@@ -48,8 +47,7 @@ def _mark(label, dev):
 
 
 def _backend():
-    if _test_backend is not None:
-        return _test_backend
+    """The CUDA library and the current device; there is nothing else to run on."""
     if not torch.cuda.is_available():
         raise RuntimeError("pythonic_disort_b200 needs a CUDA device (B200, sm_100a); it has no CPU fallback")
     return _lib.cuda_lib(), torch.device("cuda", torch.cuda.current_device())
@@ -398,6 +396,7 @@ def pydisort(
     s_poly_coeffs=np.array([[]]),
     use_banded_solver_NLayers=10,
     autograd_compatible=False,
+    _kernel_flags=0,
 ):
     """Solve the 1-D RTE for a column or a batch of columns on the GPU.
 
@@ -406,7 +405,8 @@ def pydisort(
     docstring for the batch extension.  Returns
     ``(mu_arr, flux_up, flux_down, u0)`` plus ``u`` unless ``only_flux``.
     ``use_banded_solver_NLayers`` is accepted and validated but unused (one
-    block-banded solver covers both of the reference's LAPACK paths)."""
+    block solver covers both of the reference's LAPACK paths).  ``_kernel_flags`` is a test hook: extra
+    ``pd_config.flags`` bits (``_lib.PD_FLAG_GENERIC_KERNELS`` runs the size-generic kernels)."""
     if autograd_compatible:
         raise NotImplementedError("autograd_compatible=True is not supported by the CUDA implementation.")
     lib, dev = _backend()
@@ -530,7 +530,7 @@ def pydisort(
     modes = list(BDRF_Fourier_modes)[:NFourier]
     NBDRF = len(modes)
     flags = (_lib.PD_FLAG_BEAM if beam else 0) | (_lib.PD_FLAG_ISO if Ns > 0 else 0) | \
-        (_lib.PD_FLAG_DELTA_M if f is not None else 0)
+        (_lib.PD_FLAG_DELTA_M if f is not None else 0) | (int(_kernel_flags) & _lib.PD_FLAG_GENERIC_KERNELS)
     bdrf_q = bdrf_q0 = None
     if NBDRF:
         bdrf_q, bdrf_q0, percol = _bdrf_tables(modes, B, N, mu_h, mu0_t, beam, batched, T)

@@ -25,6 +25,7 @@ struct SerialGroup {
     static constexpr int size = 1;
     PD_HD int lane() const { return 0; }
     PD_HD void sync() const {}
+    PD_HD bool any(bool v) const { return v; }
 };
 
 #if defined(__CUDACC__)
@@ -41,7 +42,16 @@ struct SubWarp {
     }
     __device__ __forceinline__ int lane() const { return ln; }
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ bool any(bool v) const { return (__ballot_sync(mask, v) & mask) != 0u; }
 };
+
+// 16 bytes global -> shared without passing through registers (L2 only: the source may have been written by this kernel)
+__device__ __forceinline__ void pd_cp_async16(double* dst_smem, const double* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void pd_cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
 #endif
 
 // padded leading dimension: odd, so that row- and column-wise lane access are both bank-conflict free

@@ -1,6 +1,4 @@
 // pd_kernel_a.cu -- stage A kernel: one lane group per (column, layer) item, one Fourier mode per blockIdx.y
-#include <stdlib.h>
-
 #include "pd_launch.h"
 #include "pd_stage_a_sym.cuh"
 
@@ -89,17 +87,10 @@ static int launch_sym(const PdStageA& a, const double* ptab, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
-static bool use_sym(int N) {
-    if (N != 4 && N != 8) return false;
-    if (const char* e = getenv("PD_STAGE_A_GENERAL"))
-        if (e[0] == '1') return false;
-    return true;
-}
-
-int pd_launch_stage_a(const PdStageA& a_in, const double* ptab, cudaStream_t st) {
+int pd_launch_stage_a(const PdStageA& a_in, int flags, const double* ptab, cudaStream_t st) {
     PdStageA a = a_in;
     a.only_flagged = 0;
-    if (use_sym(a.N)) {  // symmetric fast path first; the general kernel then only redoes flagged items
+    if ((a.N == 4 || a.N == 8) && !(flags & PD_FLAG_GENERIC_KERNELS)) {  // symmetric fast path first; the general kernel then only redoes flagged items
         const int rc = (a.N == 4) ? launch_sym<4>(a, ptab, st) : launch_sym<8>(a, ptab, st);
         if (rc) return rc;
         a.only_flagged = 1;
@@ -108,11 +99,7 @@ int pd_launch_stage_a(const PdStageA& a_in, const double* ptab, cudaStream_t st)
     const int item_doubles = (pd_stage_a_item_doubles(N, a.NLeg) + 1) & ~1;
     const size_t qbytes = (size_t)((a.NLeg * N + 1) & ~1) * 8;
     int ipc = 128 / lanes;
-    size_t cta_budget = 48 * 1024;  // shared memory per CTA: four resident CTAs pack the SM better than two when an item needs ~10 KB (N = 16; measured 439 -> 355 ms)
-    if (const char* e = getenv("PD_STAGE_A_CTA_KB")) {
-        const int v = atoi(e);
-        if (v >= 8 && v <= 200) cta_budget = (size_t)v * 1024;
-    }
+    const size_t cta_budget = 48 * 1024;  // shared memory per CTA: four resident CTAs pack the SM better than two when an item needs ~10 KB (N = 16; measured 439 -> 355 ms)
     while (ipc > 1 && qbytes + (size_t)ipc * item_doubles * 8 > cta_budget) ipc >>= 1;
     const int threads = ipc * lanes < 32 ? 32 : ipc * lanes;
     const size_t smem = qbytes + (size_t)ipc * item_doubles * 8;

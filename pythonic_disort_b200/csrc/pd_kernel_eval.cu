@@ -440,12 +440,11 @@ int pd_eval_u(const pd_config* cfg, const pd_state* st, const double* tau_q, int
         if (!omega || !f || !leg_all || !omega_s || !wleg) return -32;
         PdNT p;
         p.omega = omega; p.f = f; p.leg_all = leg_all; p.omega_s = omega_s; p.wleg = wleg;
-        // tabulated kernel for NLeg_all <= 32 (registers hold P_k(nu)); recurrence kernel otherwise or on request
-        const char* env = getenv("PD_NT_RECURRENCE");
+        // tabulated kernel for NLeg_all <= 32 (registers hold P_k(nu)); recurrence kernel otherwise or with PD_FLAG_GENERIC_KERNELS
         constexpr int NA = 32;
         const size_t smt = (size_t)(5 * a.N * a.L + NA + 2 + NA + 2 + (size_t)a.L * NA + (size_t)ntau * (5 * a.N + 1) +
                                     (ntau + 1) / 2 + 2) * 8;
-        if (a.NLeg_all <= NA && 2 * a.N * nphi <= 256 && smt <= PD_SMEM_MAX_CTA && !(env && env[0] == '1')) {
+        if (a.NLeg_all <= NA && 2 * a.N * nphi <= 256 && smt <= PD_SMEM_MAX_CTA && !(cfg->flags & PD_FLAG_GENERIC_KERNELS)) {
             e = cudaFuncSetAttribute(k_nt_tab<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smt);
             if (e != cudaSuccess) return (int)e;
             k_nt_tab<NA><<<a.B, 256, smt, pd_stream(stream)>>>(a, p, phi_q, nphi, u);

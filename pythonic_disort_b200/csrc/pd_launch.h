@@ -18,17 +18,23 @@ static inline int pd_lanes_for(int n) {
 }
 static inline cudaStream_t pd_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Stage B launch plan and workspace layout: [system flags int32 | history of k_stage_b_add | history of k_stage_b]
 struct StageBPlan {
-    int wpb, sys_doubles, blocks;
+    int add;                 // 1: k_stage_b_add runs first, k_stage_b only redoes the systems it flags
+    int add_blocks;
+    long add_slots, add_hist;  // resident systems and history doubles per system of k_stage_b_add
+    size_t flag_bytes;
+    int wpb, sys_doubles, blocks;  // k_stage_b: warps per CTA, shared doubles per system, grid
     size_t smem;
     long hist_doubles, slots;
+    size_t bytes() const { return flag_bytes + ((size_t)add_slots * add_hist + (size_t)slots * hist_doubles) * 8; }
 };
-StageBPlan pd_plan_stage_b(int B, int NF, int N, int L);
+StageBPlan pd_plan_stage_b(int B, int NF, int N, int L, int flags);
 int pd_check_cfg(const pd_config* c);
 
 // return a cudaError_t (0 = ok) or a negative argument error
-int pd_launch_stage_a(const PdStageA& a, const double* ptab, cudaStream_t st);
-int pd_launch_stage_b(const PdStageB& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int pd_launch_stage_a(const PdStageA& a, int flags, const double* ptab, cudaStream_t st);
+int pd_launch_stage_b(const PdStageB& a, int flags, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 #define PD_DISPATCH_LANES(lanes, ...)                           \
     switch (lanes) {                                            \

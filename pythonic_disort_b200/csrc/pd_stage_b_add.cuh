@@ -1,0 +1,536 @@
+// pd_stage_b_add.cuh -- boundary-condition solve of one (column, Fourier mode) system by block elimination over
+// N x N layer operators (production path for N = 2, 4, 8, 16).
+//
+// The block-banded system of _solve_for_coeffs.py:139-383 couples the 2N coefficients C_l of neighbouring layers
+// through the continuity of the 2N stream radiances at every interface.  Here the same equations are eliminated in
+// the variables "radiances at the interfaces", where the symmetry of the layer eigenvectors
+// G_l = [[V+U, V-U], [V-U, V+U]] halves the block size and removes the need for pivoting.  In the basis scaled by
+// D = diag(sqrt(w_i mu_i)) (hats):
+//      g_j = v^_j . u^_j  (< 0),      U^T V^ = diag(g)   =>   V^-1 = diag(1/g) U^T,   U^-1 = diag(1/g) V^T
+//      d_j = -tanh(k_j dtau / 2) / g_j
+//      A1 = (I + U^ d U^T)^-1,  A2 = (I + V^ d V^T)^-1          (both I + positive semidefinite)
+//      R^ = A1 - A2,   T^ = A1 + A2 - I                          (reflection / transmission of the layer, symmetric)
+//      u+_top = R^ u-_top + T^ u+_bot + s+,    u-_bot = T^ u-_top + R^ u+_bot + s-      (s: particular solutions)
+// Forward sweep (top down), stack above interface i:  u-_i = Rup_i u+_i + S_i,  Rup_0 = 0, S_0 = b_neg:
+//      (I - R^ Rup_i) [Q | q] = [T^ | R^ S_i + s+]            (Gauss-Jordan WITHOUT pivoting: energy conservation
+//      Rup_{i+1} = R^ + T^ Rup_i Q                              makes I - R^ Rup column diagonally dominant in the
+//      S_{i+1}   = T^ (Rup_i q + S_i) + s-                     flux basis; measured pivots >= 0.88 on every golden)
+// Surface:  (I - R^_s Rup_L) u+_L = R^_s S_L + b_s.   Back sweep:  u+_i = Q u+_{i+1} + q,  u-_i = Rup_i Q u+_{i+1} + (Rup_i q + S_i).
+// Coefficients of layer l from the homogeneous parts h = u - particular at its two interfaces, through the sums that
+// stay well conditioned for thin and near-conservative layers (C- + C+ and C- - C+ separately):
+//      C- + C+ = U^T (p^_top + p^_bot) / (2 g (1 + E)),   C- - C+ = V^T (d^_top + d^_bot) / (2 g (1 + E)),
+//      p = h+ + h-,  d = h+ - h-,  E = exp(-k dtau).
+// Work per layer ~ 10 N^3 flops instead of ~ 80 N^3 for the pivoted band elimination, no pivot search, and every
+// operation is a column update with all lanes busy.  The identities above hold to rounding for eigenvectors from
+// the symmetric (Cholesky + Jacobi) eigen stage; a system whose pivots or norms look wrong returns false and is
+// redone by the pivoted band solver (pd_stage_b.cuh).  tools/proto_adding.py is the NumPy prototype of this file.
+//
+// Mapping: LS = Grp::size lanes per system, lane j owns column j (+ LS, ...) of every N x N matrix and component j
+// of every vector; operands other lanes need travel through the system's shared-memory block as column-major
+// copies (broadcast reads).  The host build (tests/hostsim) runs the same code with one lane.
+#pragma once
+#include "pd_stage_b.cuh"
+
+template <int N>
+struct PdStageBAdd {
+    static_assert(N >= 2 && N % 2 == 0, "N must be even");
+    static constexpr int N2 = 2 * N, NN = N * N;
+    static constexpr int LAYER = 2 * NN + N + N2;          // one staged layer: G blocks [2][N][N], k [N], beam vector [2N]
+    static constexpr int NVEC = 8;
+    static constexpr int OFF_RING = 0;                     // [2][LAYER]
+    static constexpr int OFF_VC = OFF_RING + 2 * LAYER;    // V^ column-major; later the columns of R^ (or of R^_s)
+    static constexpr int OFF_UC = OFF_VC + NN;             // U^ column-major; later the columns of T^
+    static constexpr int OFF_WC = OFF_UC + NN;             // columns of Rup
+    static constexpr int OFF_CB = OFF_WC + NN;             // [2][2N] pivot columns (double buffered)
+    static constexpr int OFF_VEC = OFF_CB + 4 * N;         // [NVEC][N] vectors every lane needs
+    static constexpr int RAW = OFF_VEC + NVEC * N;
+    static constexpr int SD = ((RAW + 15) & ~15) + 2;      // = 2 (mod 16): the systems of a warp broadcast from distinct banks
+    static constexpr long HIST_PER_LAYER = 2 * NN + N2;    // Q^T, (Rup Q)^T, q, Rup q + S
+};
+
+#define PD_FOR_OWN(jj, j) for (int jj = 0, j = lane; jj < NJ; ++jj, j += LS)
+
+// Gauss-Jordan without pivoting on the columns a lane owns: M <- I, Y <- M^-1 Y (if WITH_Y), v <- M^-1 v.
+// `cbuf` [2][2N] shared; returns the smallest pivot seen.
+template <class Grp, int N, bool WITH_Y>
+PD_HD double pd_add_gj_solve(const Grp& g, int lane, double (&Mc)[N / Grp::size][N], double (&Y)[N / Grp::size][N],
+                             double (&vq)[N / Grp::size], double* cbuf) {
+    constexpr int LS = Grp::size, NJ = N / LS;
+    double minpiv = 1e300;
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+        double* cb = cbuf + (s & 1) * 2 * N;
+#pragma unroll
+        PD_FOR_OWN(jj, j)
+            if (j == s) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) cb[i] = Mc[jj][i];
+                cb[N] = vq[jj];
+            }
+        g.sync();
+        double f[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) f[i] = cb[i];
+        const double piv = f[s];
+        minpiv = (piv < minpiv) ? piv : minpiv;  // a NaN pivot fails the caller's test through the results
+        const double p = pd_rcp(piv);
+        const double vs = cb[N] * p;
+#pragma unroll
+        PD_FOR_OWN(jj, j) {
+            const double r = Mc[jj][s] * p;
+            double y = 0.0;
+            if (WITH_Y) y = Y[jj][s] * p;
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                if (i != s) {
+                    Mc[jj][i] = fma(-f[i], r, Mc[jj][i]);
+                    if (WITH_Y) Y[jj][i] = fma(-f[i], y, Y[jj][i]);
+                }
+            Mc[jj][s] = r;
+            if (WITH_Y) Y[jj][s] = y;
+            vq[jj] = (j == s) ? vs : fma(-cb[j], vs, vq[jj]);
+        }
+    }
+    return minpiv;
+}
+
+template <class Grp, int N>
+PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double* sm, double* hist) {
+    using F = PdStageBAdd<N>;
+    constexpr int LS = Grp::size, NJ = N / LS, N2 = 2 * N, NN = N * N;
+    static_assert(N % LS == 0, "lanes per system must divide N");
+    const int lane = g.lane();
+    const int L = A.L;
+    double* ring = sm + F::OFF_RING;
+    double* Vc = sm + F::OFF_VC;
+    double* Uc = sm + F::OFF_UC;
+    double* Wc = sm + F::OFF_WC;
+    double* cbuf = sm + F::OFF_CB;
+    double* vec = sm + F::OFF_VEC;
+    double* Rc = Vc;  // aliases: the layer operators replace the eigenvector copies once these are used up
+    double* Tc = Uc;
+
+    const long sys = (long)b * A.NF + m;
+    const double* taus = A.taus + (long)b * (L + 1);
+    const double* Kc = A.K + sys * L * N;
+    const double* Gc = A.G + sys * L * 2 * NN;
+    const double* Bc = A.beam ? A.Bv + sys * L * N2 : nullptr;
+    const double* dthc = (A.iso && m == 0) ? A.dth + (long)b * L * A.Ns * N2 : nullptr;
+    const double mu0 = A.colp[(long)b * PD_NCOLP + PD_COL_MU0];
+    const double I0 = A.colp[(long)b * PD_NCOLP + PD_COL_I0];
+    const bool beam = A.beam && I0 > 0.0;
+    const bool has_bdrf = A.NBDRF > m;
+    const bool have_b = (m == 0) || (A.NFb > 1);
+    const double* bpos = A.bpos + ((long)b * A.NFb + (A.NFb > 1 ? m : 0)) * N;
+    const double* bneg = A.bneg + ((long)b * A.NFb + (A.NFb > 1 ? m : 0)) * N;
+    const double rmu0 = beam ? 1.0 / mu0 : 0.0;
+    bool bad = false;
+
+    // layer ll (G blocks, k, beam vector) -> ring slot ll & 1
+    auto stage = [&](int ll) {
+        double* dst = ring + (ll & 1) * F::LAYER;
+        const double* gs = Gc + (long)ll * 2 * NN;
+        const double* ks = Kc + (long)ll * N;
+#if defined(__CUDA_ARCH__)
+        for (int ch = lane; ch < NN; ch += LS) pd_cp_async16(dst + 2 * ch, gs + 2 * ch);
+        for (int ch = lane; ch < N / 2; ch += LS) pd_cp_async16(dst + 2 * NN + 2 * ch, ks + 2 * ch);
+        if (Bc)
+            for (int ch = lane; ch < N; ch += LS) pd_cp_async16(dst + 2 * NN + N + 2 * ch, Bc + (long)ll * N2 + 2 * ch);
+#else
+        for (int i = 0; i < 2 * NN; ++i) dst[i] = gs[i];
+        for (int i = 0; i < N; ++i) dst[2 * NN + i] = ks[i];
+        if (Bc)
+            for (int i = 0; i < N2; ++i) dst[2 * NN + N + i] = Bc[(long)ll * N2 + i];
+#endif
+    };
+    auto stage_wait = [&]() {
+#if defined(__CUDA_ARCH__)
+        pd_cp_async_wait_all();
+#endif
+        g.sync();
+    };
+    // rows j of V^ = D (Gp + Gm) / 2 and U^ = D (Gp - Gm) / 2 -> column-major copies in shared memory (+ sync)
+    double Dj[NJ];
+#pragma unroll
+    PD_FOR_OWN(jj, j) Dj[jj] = sqrt(A.w[j] * A.mu[j]);
+    auto eigvec_columns = [&](const double* Gl, double (&vrow)[NJ][N], double (&urow)[NJ][N]) {
+#pragma unroll
+        PD_FOR_OWN(jj, j) {
+            const double h = 0.5 * Dj[jj];
+#pragma unroll
+            for (int k = 0; k < N; k += 2) {
+                const pd_d2 gp = *reinterpret_cast<const pd_d2*>(Gl + j * N + k);
+                const pd_d2 gm = *reinterpret_cast<const pd_d2*>(Gl + NN + j * N + k);
+                vrow[jj][k] = h * (gp.x + gm.x);
+                vrow[jj][k + 1] = h * (gp.y + gm.y);
+                urow[jj][k] = h * (gp.x - gm.x);
+                urow[jj][k + 1] = h * (gp.y - gm.y);
+            }
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                Vc[k * N + j] = vrow[jj][k];
+                Uc[k * N + j] = urow[jj][k];
+            }
+        }
+        g.sync();
+    };
+    // y_j = sum_i col[i] x[i], x broadcast from shared memory
+    auto dot_own = [&](const double (&col)[N], const double* x) -> double {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            const pd_d2 xv = *reinterpret_cast<const pd_d2*>(x + i);
+            s0 = fma(col[i], xv.x, s0);
+            s1 = fma(col[i + 1], xv.y, s1);
+        }
+        return s0 + s1;
+    };
+    // acc[:] += sum_k Mc[:, k] * coef[k], columns of Mc broadcast from shared memory (column-major)
+    auto add_cols = [&](double (&acc)[N], const double* Mcm, const double (&coef)[N]) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const double c = coef[k];
+#pragma unroll
+            for (int i = 0; i < N; i += 2) {
+                const pd_d2 mv = *reinterpret_cast<const pd_d2*>(Mcm + k * N + i);
+                acc[i] = fma(mv.x, c, acc[i]);
+                acc[i + 1] = fma(mv.y, c, acc[i + 1]);
+            }
+        }
+    };
+    // particular solution of layer l (hat basis) at the top (tau*_l, attenuation at) and bottom (tau*_{l+1}, ab)
+    auto particular = [&](int l, const double* Bl, double at, double ab, double (&ptp)[NJ], double (&ptm)[NJ],
+                          double (&pbp)[NJ], double (&pbm)[NJ]) {
+#pragma unroll
+        PD_FOR_OWN(ii, i) {
+            double a = 0.0, c = 0.0, d = 0.0, e = 0.0;
+            if (beam) {
+                a = Bl[i] * at;
+                c = Bl[N + i] * at;
+                d = Bl[i] * ab;
+                e = Bl[N + i] * ab;
+            }
+            if (dthc) {
+                const double* dl = dthc + (long)l * A.Ns * N2;
+                a += pd_thermal_at(dl, A.Ns, N2, i, taus[l]);
+                c += pd_thermal_at(dl, A.Ns, N2, N + i, taus[l]);
+                d += pd_thermal_at(dl, A.Ns, N2, i, taus[l + 1]);
+                e += pd_thermal_at(dl, A.Ns, N2, N + i, taus[l + 1]);
+            }
+            ptp[ii] = Dj[ii] * a;
+            ptm[ii] = Dj[ii] * c;
+            pbp[ii] = Dj[ii] * d;
+            pbm[ii] = Dj[ii] * e;
+        }
+    };
+
+    // ---------------------------------------------------------------- forward sweep
+    double Rup[NJ][N], S[NJ];
+#pragma unroll
+    PD_FOR_OWN(jj, j) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            Rup[jj][i] = 0.0;
+            Wc[j * N + i] = 0.0;
+        }
+        S[jj] = Dj[jj] * (have_b ? bneg[j] : 0.0);
+    }
+    stage(0);
+    double att_t = 1.0;  // exp(-tau*_l / mu0), tau*_0 = 0
+    for (int l = 0; l < L; ++l) {
+        stage_wait();
+        if (l + 1 < L) stage(l + 1);
+        const double* Gl = ring + (l & 1) * F::LAYER;
+        const double* Kl = Gl + 2 * NN;
+        const double* Bl = Kl + N;
+        const double dtau = taus[l + 1] - taus[l];
+        const double att_b = beam ? exp(-taus[l + 1] * rmu0) : 0.0;
+
+        double Rh[NJ][N], Th[NJ][N];
+        {
+            double vrow[NJ][N], urow[NJ][N];
+            eigvec_columns(Gl, vrow, urow);
+            // d_k = -tanh(k dtau / 2) / g_k by the lane that owns k
+#pragma unroll
+            PD_FOR_OWN(kk, k) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int i = 0; i < N; i += 2) {
+                    const pd_d2 v2 = *reinterpret_cast<const pd_d2*>(Vc + k * N + i);
+                    const pd_d2 u2 = *reinterpret_cast<const pd_d2*>(Uc + k * N + i);
+                    s0 = fma(v2.x, u2.x, s0);
+                    s1 = fma(v2.y, u2.y, s1);
+                }
+                const double gk = s0 + s1;
+                const double em = expm1(-Kl[k] * dtau);  // tanh(x / 2) = -expm1(-x) / (2 + expm1(-x))
+                const double dk = (em / (2.0 + em)) / gk;
+                bad = bad || !(gk < 0.0) || !(dk >= 0.0);
+                vec[k] = dk;
+            }
+            g.sync();
+            // columns j of I + U^ d U^T and I + V^ d V^T
+            double X1[NJ][N], X2[NJ][N];
+#pragma unroll
+            PD_FOR_OWN(jj, j) {
+                double c1[N], c2[N];
+#pragma unroll
+                for (int k = 0; k < N; k += 2) {
+                    const pd_d2 d2 = *reinterpret_cast<const pd_d2*>(vec + k);
+                    c1[k] = d2.x * urow[jj][k];
+                    c1[k + 1] = d2.y * urow[jj][k + 1];
+                    c2[k] = d2.x * vrow[jj][k];
+                    c2[k + 1] = d2.y * vrow[jj][k + 1];
+                }
+#pragma unroll
+                for (int i = 0; i < N; ++i) X1[jj][i] = X2[jj][i] = (i == j) ? 1.0 : 0.0;
+                add_cols(X1[jj], Uc, c1);
+                add_cols(X2[jj], Vc, c2);
+            }
+            // both inverses in place, interleaved (Gauss-Jordan; the pivots of I + PSD are >= 1)
+#pragma unroll
+            for (int s = 0; s < N; ++s) {
+                double* cb = cbuf + (s & 1) * 2 * N;
+#pragma unroll
+                PD_FOR_OWN(jj, j)
+                    if (j == s) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            cb[i] = X1[jj][i];
+                            cb[N + i] = X2[jj][i];
+                        }
+                    }
+                g.sync();
+                double f1[N], f2[N];
+#pragma unroll
+                for (int i = 0; i < N; i += 2) {
+                    const pd_d2 a2 = *reinterpret_cast<const pd_d2*>(cb + i);
+                    const pd_d2 b2 = *reinterpret_cast<const pd_d2*>(cb + N + i);
+                    f1[i] = a2.x; f1[i + 1] = a2.y; f2[i] = b2.x; f2[i + 1] = b2.y;
+                }
+                const double p1 = pd_rcp(f1[s]), p2 = pd_rcp(f2[s]);
+#pragma unroll
+                PD_FOR_OWN(jj, j) {
+                    const bool own = (j == s);  // the eliminated column is replaced by that of the inverse
+                    const double r1 = (own ? 1.0 : X1[jj][s]) * p1;
+                    const double r2 = (own ? 1.0 : X2[jj][s]) * p2;
+#pragma unroll
+                    for (int i = 0; i < N; ++i)
+                        if (i != s) {
+                            X1[jj][i] = fma(-f1[i], r1, own ? 0.0 : X1[jj][i]);
+                            X2[jj][i] = fma(-f2[i], r2, own ? 0.0 : X2[jj][i]);
+                        }
+                    X1[jj][s] = r1;
+                    X2[jj][s] = r2;
+                }
+            }
+            // R^ = A1 - A2, T^ = A1 + A2 - I; their columns replace the eigenvector copies
+#pragma unroll
+            PD_FOR_OWN(jj, j) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    Rh[jj][i] = X1[jj][i] - X2[jj][i];
+                    Th[jj][i] = X1[jj][i] + X2[jj][i] - ((i == j) ? 1.0 : 0.0);
+                    Rc[j * N + i] = Rh[jj][i];
+                    Tc[j * N + i] = Th[jj][i];
+                }
+            }
+        }
+        // source terms
+        double ptp[NJ], ptm[NJ], pbp[NJ], pbm[NJ];
+        particular(l, Bl, att_t, att_b, ptp, ptm, pbp, pbm);
+#pragma unroll
+        PD_FOR_OWN(ii, i) {
+            vec[N + i] = ptm[ii];
+            vec[2 * N + i] = pbp[ii];
+            vec[3 * N + i] = S[ii];
+        }
+        g.sync();
+        double sminus[NJ], vq[NJ], Mc[NJ][N], Y[NJ][N];
+#pragma unroll
+        PD_FOR_OWN(jj, j) {
+            // rows j of the symmetric R^, T^ are the columns this lane holds
+            const double splus = ptp[jj] - dot_own(Rh[jj], vec + N) - dot_own(Th[jj], vec + 2 * N);
+            sminus[jj] = pbm[jj] - dot_own(Th[jj], vec + N) - dot_own(Rh[jj], vec + 2 * N);
+            vq[jj] = splus + dot_own(Rh[jj], vec + 3 * N);
+            double coef[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                Mc[jj][i] = (i == j) ? 1.0 : 0.0;
+                Y[jj][i] = Th[jj][i];
+                coef[i] = -Rup[jj][i];
+            }
+            add_cols(Mc[jj], Rc, coef);  // column j of I - R^ Rup
+        }
+        const double mp = pd_add_gj_solve<Grp, N, true>(g, lane, Mc, Y, vq, cbuf);
+        bad = bad || !(mp > 0.05);
+        // Y = Q (columns), vq = q
+#pragma unroll
+        PD_FOR_OWN(ii, i) vec[4 * N + i] = vq[ii];
+        g.sync();
+        double RQ[NJ][N], rs[NJ];
+#pragma unroll
+        PD_FOR_OWN(jj, j) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) RQ[jj][i] = 0.0;
+            add_cols(RQ[jj], Wc, Y[jj]);
+            rs[jj] = S[jj] + dot_own(Rup[jj], vec + 4 * N);
+            vec[5 * N + j] = rs[jj];
+        }
+        g.sync();  // also: every lane is done with the columns of Rup in Wc
+        double* hl = hist + (long)l * F::HIST_PER_LAYER;
+#pragma unroll
+        PD_FOR_OWN(jj, j) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                hl[j * N + i] = Y[jj][i];
+                hl[NN + j * N + i] = RQ[jj][i];
+            }
+            hl[2 * NN + j] = vq[jj];
+            hl[2 * NN + N + j] = rs[jj];
+#pragma unroll
+            for (int i = 0; i < N; ++i) Rup[jj][i] = Rh[jj][i];
+            add_cols(Rup[jj], Tc, RQ[jj]);
+            S[jj] = sminus[jj] + dot_own(Th[jj], vec + 5 * N);
+#pragma unroll
+            for (int i = 0; i < N; ++i) Wc[j * N + i] = Rup[jj][i];
+        }
+        att_t = att_b;
+    }
+    g.sync();
+
+    // ---------------------------------------------------------------- surface  (_solve_for_coeffs.py:121-134, :163, :248-254)
+    double ubp[NJ], ubm[NJ];  // u^+ and u^- at the bottom interface of the current layer
+    {
+        double bs[NJ];
+#pragma unroll
+        PD_FOR_OWN(ii, i) {
+            double v = have_b ? bpos[i] : 0.0;
+            if (beam && has_bdrf) {
+                const double* q0 = A.bdrf_q0 + ((A.bdrf_percol ? (long)b * A.NBDRF : 0) + m) * N;
+                v = fma((mu0 * I0 / PD_PI) * q0[i], att_t, v);
+            }
+            bs[ii] = Dj[ii] * v;
+        }
+        if (has_bdrf) {
+            // R^_s[i][k] = (1 + delta_m0) q[i][k] D_i D_k, stored column-major where R^ was
+            const double* qm = A.bdrf_q + ((A.bdrf_percol ? (long)b * A.NBDRF : 0) + m) * NN;
+            const double fac = (m == 0) ? 2.0 : 1.0;
+            for (int idx = lane; idx < NN; idx += LS) {
+                const int k = idx / N, i = idx - k * N;
+                Rc[idx] = fac * qm[i * N + k] * sqrt(A.w[i] * A.mu[i] * A.w[k] * A.mu[k]);
+            }
+#pragma unroll
+            PD_FOR_OWN(ii, i) vec[i] = S[ii];
+            g.sync();
+            double Mc[NJ][N], Y[NJ][N], vq[NJ];
+#pragma unroll
+            PD_FOR_OWN(jj, j) {
+                double coef[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    Mc[jj][i] = (i == j) ? 1.0 : 0.0;
+                    Y[jj][i] = 0.0;
+                    coef[i] = -Rup[jj][i];
+                }
+                add_cols(Mc[jj], Rc, coef);  // column j of I - R^_s Rup
+                double s = bs[jj];           // row j of R^_s times S
+#pragma unroll
+                for (int k = 0; k < N; ++k) s = fma(Rc[k * N + j], vec[k], s);
+                vq[jj] = s;
+            }
+            const double mp = pd_add_gj_solve<Grp, N, false>(g, lane, Mc, Y, vq, cbuf);
+            bad = bad || !(mp > 0.01);
+#pragma unroll
+            PD_FOR_OWN(ii, i) ubp[ii] = vq[ii];
+        } else {
+#pragma unroll
+            PD_FOR_OWN(ii, i) ubp[ii] = bs[ii];
+        }
+#pragma unroll
+        PD_FOR_OWN(ii, i) vec[N + i] = ubp[ii];
+        g.sync();
+#pragma unroll
+        PD_FOR_OWN(ii, i) ubm[ii] = S[ii] + dot_own(Rup[ii], vec + N);
+    }
+
+    // ---------------------------------------------------------------- back sweep
+    double* Cout = A.C + sys * L * N2;
+    double Qr[NJ][N], RQr[NJ][N], qi[NJ], rsi[NJ];
+    auto load_history = [&](int l) {
+        const double* hl = hist + (long)l * F::HIST_PER_LAYER;
+#pragma unroll
+        PD_FOR_OWN(ii, i) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                Qr[ii][j] = hl[j * N + i];
+                RQr[ii][j] = hl[NN + j * N + i];
+            }
+            qi[ii] = hl[2 * NN + i];
+            rsi[ii] = hl[2 * NN + N + i];
+        }
+    };
+    load_history(L - 1);
+    double att_b = att_t;  // exp(-tau*_L / mu0)
+    for (int l = L - 1; l >= 0; --l) {
+        if (l != L - 1) stage_wait();
+        else g.sync();
+        if (l > 0) stage(l - 1);
+        const double* Gl = ring + (l & 1) * F::LAYER;
+        const double* Kl = Gl + 2 * NN;
+        const double* Bl = Kl + N;
+        const double dtau = taus[l + 1] - taus[l];
+        const double at = beam ? exp(-taus[l] * rmu0) : 0.0;
+#pragma unroll
+        PD_FOR_OWN(ii, i) vec[i] = ubp[ii];
+        g.sync();
+        double utp[NJ], utm[NJ];
+#pragma unroll
+        PD_FOR_OWN(ii, i) {
+            utp[ii] = qi[ii] + dot_own(Qr[ii], vec);
+            utm[ii] = rsi[ii] + dot_own(RQr[ii], vec);
+        }
+        if (l > 0) load_history(l - 1);  // in flight while this layer's coefficients are recovered
+        double vrow[NJ][N], urow[NJ][N];
+        eigvec_columns(Gl, vrow, urow);
+        double ptp[NJ], ptm[NJ], pbp[NJ], pbm[NJ];
+        particular(l, Bl, at, att_b, ptp, ptm, pbp, pbm);
+#pragma unroll
+        PD_FOR_OWN(ii, i) {
+            const double htp = utp[ii] - ptp[ii], htm = utm[ii] - ptm[ii];
+            const double hbp = ubp[ii] - pbp[ii], hbm = ubm[ii] - pbm[ii];
+            vec[N + i] = (htp + htm) + (hbp + hbm);
+            vec[2 * N + i] = (htp - htm) + (hbp - hbm);
+        }
+        g.sync();
+#pragma unroll
+        PD_FOR_OWN(kk, k) {
+            double g0 = 0.0, g1 = 0.0, s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; i += 2) {
+                const pd_d2 v2 = *reinterpret_cast<const pd_d2*>(Vc + k * N + i);
+                const pd_d2 u2 = *reinterpret_cast<const pd_d2*>(Uc + k * N + i);
+                const pd_d2 ps = *reinterpret_cast<const pd_d2*>(vec + N + i);
+                const pd_d2 ds = *reinterpret_cast<const pd_d2*>(vec + 2 * N + i);
+                g0 = fma(v2.x, u2.x, g0);
+                g1 = fma(v2.y, u2.y, g1);
+                s0 = fma(u2.x, ps.x, s0);
+                s1 = fma(u2.y, ps.y, s1);
+                t0 = fma(v2.x, ds.x, t0);
+                t1 = fma(v2.y, ds.y, t1);
+            }
+            const double E = exp(-Kl[k] * dtau);
+            const double sc = 0.25 / ((g0 + g1) * (1.0 + E));  // (1 / (2 g (1 + E))) / 2
+            const double ss = (s0 + s1) * sc, tt = (t0 + t1) * sc;
+            Cout[(long)l * N2 + k] = ss + tt;
+            Cout[(long)l * N2 + N + k] = ss - tt;
+            bad = bad || !(fabs(ss) + fabs(tt) < 1e300);
+        }
+#pragma unroll
+        PD_FOR_OWN(ii, i) {
+            ubp[ii] = utp[ii];
+            ubm[ii] = utm[ii];
+        }
+        att_b = at;
+    }
+    return !g.any(bad);
+}

@@ -15,17 +15,32 @@
 #include "../../pythonic_disort_b200/csrc/pd_stage_a.cuh"
 #include "../../pythonic_disort_b200/csrc/pd_stage_a_sym.cuh"
 #include "../../pythonic_disort_b200/csrc/pd_stage_b.cuh"
+#include "../../pythonic_disort_b200/csrc/pd_stage_b_add.cuh"
+
+template <int N>
+static bool host_stage_b_add(const PdStageB& sb, int b, int m, double* hist) {
+    SerialGroup g;
+    double* sm = (double*)malloc(sizeof(double) * PdStageBAdd<N>::SD);
+    const bool ok = pd_stage_b_add<SerialGroup, N>(g, sb, b, m, sm, hist);
+    free(sm);
+    return ok;
+}
 
 extern "C" {
 
 int pd_abi_version(void) { return PD_ABI_VERSION; }
 int pd_is_hostsim(void) { return 1; }
-static long g_sym_done = 0, g_general = 0;
-long pd_hostsim_count(int which) { return which ? g_general : g_sym_done; }
-void pd_hostsim_reset(void) { g_sym_done = g_general = 0; }
+static long g_sym_done = 0, g_general = 0, g_bc_add = 0, g_bc_band = 0;
+// which: 0 symmetric eigen items, 1 general eigen items, 2 systems solved by the adding stage B, 3 by the band solver
+long pd_hostsim_count(int which) { return which == 0 ? g_sym_done : which == 1 ? g_general : which == 2 ? g_bc_add : g_bc_band; }
+void pd_hostsim_reset(void) { g_sym_done = g_general = g_bc_add = g_bc_band = 0; }
+
+static long add_hist_doubles(int N, int L) { return (long)L * (2 * N * N + 2 * N); }
 
 size_t pd_workspace_bytes(const pd_config* cfg) {
-    return (size_t)pd_stage_b_history_doubles(cfg->NQuad / 2, cfg->L) * 8;
+    const int N = cfg->NQuad / 2;
+    const long a = pd_stage_b_history_doubles(N, cfg->L), b = add_hist_doubles(N, cfg->L);
+    return (size_t)(a > b ? a : b) * 8;
 }
 
 int pd_prologue(const pd_config* cfg, const double* tau, const double* omega, const double* leg_all, const double* f,
@@ -67,8 +82,8 @@ int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const 
         for (int idx = 0; idx < nm * N; ++idx)
             Q[idx] = ptab[((long)m * cfg->NLeg + m) * N + idx] * sqrt(w_nodes[idx % N] / mu_nodes[idx % N]);
         // same dispatch as pd_launch_stage_a: symmetric one-thread-per-item path for N = 4, 8 (unless
-        // PD_STAGE_A_GENERAL=1), general Hessenberg-QR path otherwise and for flagged items
-        const bool sym = (N == 4 || N == 8) && !(getenv("PD_STAGE_A_GENERAL") && getenv("PD_STAGE_A_GENERAL")[0] == '1');
+        // PD_FLAG_GENERIC_KERNELS), general Hessenberg-QR path otherwise and for flagged items
+        const bool sym = (N == 4 || N == 8) && !(cfg->flags & PD_FLAG_GENERIC_KERNELS);
         const int NPk = N * (N + 1) / 2;
         double* QQ = (double*)malloc(sizeof(double) * (nm * NPk + 1));
         double* park = (double*)malloc(sizeof(double) * (NPk + 3 * N + 1));
@@ -99,8 +114,24 @@ int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const 
     sb.bdrf_q = bdrf_q; sb.bdrf_q0 = bdrf_q0; sb.K = K; sb.G = G; sb.Bv = Bv; sb.dth = dth; sb.C = C;
     sb.status = status;
     double* smb = (double*)malloc(sizeof(double) * (pd_stage_b_doubles(N) + 16));
+    // same dispatch as pd_launch_stage_b: interface-radiance elimination for N = 2, 4, 8, 16 (unless
+    // PD_FLAG_GENERIC_KERNELS), pivoted band solver otherwise and for the systems the first one hands back
+    const bool generic_b = (cfg->flags & PD_FLAG_GENERIC_KERNELS) != 0;
     for (int b = 0; b < cfg->B; ++b)
-        for (int m = 0; m < cfg->NFourier; ++m) pd_stage_b_system(g, sb, b, m, smb, (double*)workspace);
+        for (int m = 0; m < cfg->NFourier; ++m) {
+            bool ok = false;
+            if (!generic_b) {
+                if (N == 2) ok = host_stage_b_add<2>(sb, b, m, (double*)workspace);
+                if (N == 4) ok = host_stage_b_add<4>(sb, b, m, (double*)workspace);
+                if (N == 8) ok = host_stage_b_add<8>(sb, b, m, (double*)workspace);
+                if (N == 16) ok = host_stage_b_add<16>(sb, b, m, (double*)workspace);
+            }
+            if (ok) ++g_bc_add;
+            else {
+                ++g_bc_band;
+                pd_stage_b_system(g, sb, b, m, smb, (double*)workspace);
+            }
+        }
     free(smb);
     return 0;
 }

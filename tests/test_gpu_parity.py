@@ -15,7 +15,7 @@ import pytest
 import golden_io
 import parity_suite
 import pythonic_disort_b200 as pd
-from pythonic_disort_b200 import api, synthetic
+from pythonic_disort_b200 import _lib, api, synthetic
 
 pytestmark = pytest.mark.gpu
 SUITE = golden_io.suite_names()
@@ -25,7 +25,8 @@ SUITE = golden_io.suite_names()
 def cuda_backend():
     import torch
     assert torch.cuda.is_available()
-    assert api._test_backend is None, "GPU tests must run the CUDA library, not the host build"
+    lib, dev = api._backend()
+    assert dev.type == "cuda" and not hasattr(lib, "pd_is_hostsim"), "GPU tests must run the CUDA library, not the host build"
     yield
 
 
@@ -131,47 +132,39 @@ def test_cuda_tensor_inputs_give_cuda_outputs():
     np.testing.assert_allclose(Fp.cpu().numpy(), ref["flux_up"], rtol=1e-14)
 
 
-@pytest.mark.parametrize("env", [
-    {"PD_STAGE_A_GENERAL": "1"},                              # Hessenberg-QR eigen kernel instead of Cholesky+Jacobi
-    {"PD_STAGE_B_MMA": "0"},                                  # three-rows-per-lane register kernel instead of the tensor-core one
-    {"PD_STAGE_B_MMA": "0", "PD_STAGE_B_ROW1": "1"},          # one-row-per-lane register kernel (shuffle broadcast)
-    {"PD_STAGE_B_MMA": "0", "PD_STAGE_B_ROW1": "1", "PD_STAGE_B_SHFL": "0"},         # ... shared-memory broadcast
-    {"PD_NT_RECURRENCE": "1"},                                # NT corrections by per-output recurrences (any NLeg_all)
-    {"PD_STAGE_B_SMEM": "1"},                                 # shared-memory panel kernel instead of register rows
-    {"PD_STAGE_B_SMEM": "1", "PD_STAGE_B_LS": "16"},          # ... two systems per warp
-    {"PD_STAGE_B_GENERIC": "1", "PD_STAGE_A_GENERAL": "1"},   # size-generic kernels (what any other NQuad uses)
-])
+def _generic(*args, **kwargs):
+    """pydisort() on the size-generic kernels (pd_config.flags test bit, include/pydisort_b200.h)."""
+    return pd.pydisort(*args, _kernel_flags=_lib.PD_FLAG_GENERIC_KERNELS, **kwargs)
+
+
 @pytest.mark.parametrize("name", ["sw", "lw", "tp9c"])
-def test_every_kernel_variant_meets_the_same_bar(monkeypatch, env, name):
-    """The production shapes have specialised kernels; the general ones are the fallback and serve every other
-    NQuad.  All of them must reproduce the reference."""
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
+def test_generic_kernels_meet_the_same_bar(name):
+    """The production shapes have specialised kernels (symmetric eigen stage, interface-radiance elimination,
+    tabulated NT); the size-generic ones (Hessenberg-QR, pivoted band solver, per-output recurrences) serve every
+    other NQuad and are the fallback.  Both must reproduce the reference."""
     if name == "tp9c":
         from oracle import disort_oracle
         ens = synthetic.make(name, 2)
-        got = parity_suite.run_batched(pd.pydisort, ens)
+        got = parity_suite.run_batched(_generic, ens)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             ref = synthetic.run_reference_like(disort_oracle.pydisort, ens)
         parity_suite.compare_fields(got, ref, 2, 1e-9, name)
     else:
-        parity_suite.check_ensemble_vs_golden(pd.pydisort, name)
+        parity_suite.check_ensemble_vs_golden(_generic, name)
 
 
 @pytest.mark.parametrize("name,ncol,first", [("sw", 4096, 20000), ("ha", 96, 500), ("lw", 8192, 100000)])
-def test_production_kernels_agree_with_the_generic_ones_on_large_slices(monkeypatch, name, ncol, first):
-    """Thousands of columns the oracle would take minutes for: the specialised kernels (symmetric stage A, tensor-core /
-    register stage B, tabulated NT) against the size-generic ones (Hessenberg-QR, shared-memory panel with Gaussian
-    elimination + triangular solves, per-output recurrences).  Two independent implementations of the same equations,
-    different pivot bookkeeping and summation orders: they must agree within the parity bar on every column (typical
-    agreement is 1e-13; columns where 1/mu0 falls next to an eigenvalue k of a layer are conditioned like
-    1/(1/mu0^2 - k^2) and move by ~1e-10 between ANY two implementations, the oracle included)."""
+def test_production_kernels_agree_with_the_generic_ones_on_large_slices(name, ncol, first):
+    """Thousands of columns the oracle would take minutes for: the specialised kernels (symmetric stage A, pivot-free
+    elimination over interface radiances, tabulated NT) against the size-generic ones (Hessenberg-QR, pivoted band
+    elimination of the coefficients, per-output recurrences).  Two independent formulations of the same equations:
+    they must agree within the parity bar on every column (typical agreement is 1e-13; columns where 1/mu0 falls
+    next to an eigenvalue k of a layer are conditioned like 1/(1/mu0^2 - k^2) and move by ~1e-10 between ANY two
+    implementations, the oracle included).  NOT a parity test: it compares the CUDA path with itself."""
     ens = synthetic.make(name, ncol, first)
     got = parity_suite.run_batched(pd.pydisort, ens)
-    for k, v in {"PD_STAGE_B_GENERIC": "1", "PD_STAGE_A_GENERAL": "1", "PD_NT_RECURRENCE": "1"}.items():
-        monkeypatch.setenv(k, v)
-    ref = parity_suite.run_batched(pd.pydisort, ens)
+    ref = parity_suite.run_batched(_generic, ens)
     tol = golden_io.conditioning_tolerance(ens["args"][1], 1e-9)
     worst, _, _ = parity_suite.compare_fields(got, ref, ncol, tol, name + " production vs generic kernels")
     assert worst < tol

@@ -48,30 +48,27 @@ def test_hapke_fourier_modes():
     parity_suite.check_hapke_modes_vs_golden(pd)
 
 
-def _counts(lib):
-    import ctypes
-    lib.pd_hostsim_count.restype = ctypes.c_long
-    return lib.pd_hostsim_count(0), lib.pd_hostsim_count(1)
+def test_production_paths_cover_the_production_shapes_and_match_the_generic_kernels():
+    """N = 4 / 8 items go through the Cholesky + Jacobi path and every system through the interface-radiance
+    elimination (no hand-backs on the ensembles); the size-generic kernels (PD_FLAG_GENERIC_KERNELS) give the same
+    answers."""
+    from pythonic_disort_b200 import _lib, api, synthetic
+    lib = api._backend()[0]
+    lib.pd_hostsim_count.restype = __import__("ctypes").c_long
 
+    def generic(*args, **kwargs):
+        return pd.pydisort(*args, _kernel_flags=_lib.PD_FLAG_GENERIC_KERNELS, **kwargs)
 
-def test_symmetric_eigen_path_covers_the_production_shapes_and_matches_the_general_path(monkeypatch):
-    """N = 4 / 8 items go through the Cholesky + Jacobi path (no fallbacks on the ensembles);
-    forcing the general Hessenberg-QR path gives the same answers."""
-    import warnings
-
-    from pythonic_disort_b200 import api, synthetic
-    lib = api._test_backend[0]
     for name, ncol in (("sw", 3), ("lw", 6)):
         ens = synthetic.make(name, ncol)
         lib.pd_hostsim_reset()
         fast = parity_suite.run_batched(pd.pydisort, ens)
-        sym, general = _counts(lib)
-        assert sym > 0 and general == 0, (name, sym, general)
-        monkeypatch.setenv("PD_STAGE_A_GENERAL", "1")
+        counts = [lib.pd_hostsim_count(i) for i in range(4)]
+        assert counts[0] > 0 and counts[1] == 0 and counts[2] > 0 and counts[3] == 0, (name, counts)
         lib.pd_hostsim_reset()
-        slow = parity_suite.run_batched(pd.pydisort, ens)
-        assert _counts(lib)[0] == 0
-        monkeypatch.delenv("PD_STAGE_A_GENERAL")
+        slow = parity_suite.run_batched(generic, ens)
+        counts = [lib.pd_hostsim_count(i) for i in range(4)]
+        assert counts[0] == 0 and counts[2] == 0, (name, counts)
         for key in fast:
             scale = np.max(np.abs(slow[key]))
             assert np.max(np.abs(fast[key] - slow[key])) <= 1e-11 * scale, (name, key)
