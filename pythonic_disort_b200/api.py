@@ -36,6 +36,7 @@ from .subroutines import Gauss_Legendre_quad, TabulatedBDRF
 
 _F64 = torch.float64
 _const_cache = {}
+_interp_cache = {}
 _profile = None  # bench.py sets this to a list to collect (label, CUDA event) marks around each launch
 
 
@@ -128,9 +129,27 @@ class _Solution:
         else:
             raise ValueError("tau must be a scalar, a 1-D array, or (batch mode) a [B, ntau] array.")
         tq = tq.contiguous()
-        if bool(((tq < 0) | (tq > self.tau[:, -1:])).any()):
-            raise ValueError("tau input outside the tau range given for the atmosphere (check `tau_arr`).")
+        if isinstance(tau, torch.Tensor) and tau.is_cuda or self.defer is not None:
+            # device-resident query points: the range test runs on the device and is read back with the results
+            # (or, in a pipelined ensemble solve, once after the last chunk) -- no stream drain here
+            self._note("tau_range", ((tq < 0) | (tq > self.tau[:, -1:])).any())
+        else:
+            th = tau.detach().cpu().numpy() if isinstance(tau, torch.Tensor) else np.asarray(tau, dtype=np.float64)
+            if self._tau_max is None:
+                self._tau_max = self.tau[:, -1].cpu().numpy()
+            over = np.any(th > self._tau_max[:, None]) if th.ndim == 2 else np.max(th, initial=0.0) > self._tau_max.min()
+            if np.any(th < 0) or over:
+                raise ValueError("tau input outside the tau range given for the atmosphere (check `tau_arr`).")
         return tq, scalar
+
+    def _note(self, kind, flag):
+        """Queue a device-side check; `raise_pending` turns it into the reference's exception."""
+        (self.defer if self.defer is not None else self.pending).append((kind, flag))
+
+    def raise_pending(self):
+        if self.pending:
+            pending, self.pending[:] = list(self.pending), []
+            _raise_for_pending(pending)
 
     def _finish(self, out, ref_dims):
         """Squeeze like the reference (``np.squeeze(x)[()]``) but never the batch axis."""
@@ -139,6 +158,8 @@ class _Solution:
         if not self.batched:
             out = out[0]
         if self.want_torch:
+            if self.pending:
+                self.raise_pending()
             return out
         if out.is_cuda and out.numel() >= 1 << 16:
             # large result: device -> pinned host buffer (torch's caching host allocator recycles it once the
@@ -165,7 +186,11 @@ class _Solution:
     # -- launches ----------------------------------------------------------------
     def interp_mu(self, vals, mu):
         """``vals`` [B, 2N, ...] on the device -> [B, nmu, ...] at the polar-angle cosines ``mu`` (row f1)."""
-        W = torch.as_tensor(barycentric_weight_matrix(mu, self.NQuad // 2), dtype=_F64, device=self.dev).contiguous()
+        key = (tuple(np.atleast_1d(np.asarray(mu, dtype=np.float64)).tolist()), self.NQuad, str(self.dev))
+        if key not in _interp_cache:
+            _interp_cache[key] = torch.as_tensor(barycentric_weight_matrix(mu, self.NQuad // 2), dtype=_F64,
+                                                 device=self.dev).contiguous()
+        W = _interp_cache[key]
         nmu = W.shape[0]
         vals = vals.contiguous()
         M = int(np.prod(vals.shape[2:])) if vals.ndim > 2 else 1
@@ -315,21 +340,33 @@ def barycentric_weight_matrix(mu, N):
     return W
 
 
-def _bc_tensor(b, name, B, N, NF, batched, T):
-    """Dirichlet boundary values as [B, NFb, N] (pydisort.py:199-202, :274-285)."""
+def _bc_tensor(b, name, B, N, NF, batched, T, is_zero=None):
+    """Dirichlet boundary values as [B, NFb, N] (pydisort.py:199-202, :274-285).
+
+    Reference shapes: scalar, [N] (mode 0) or [N, NFourier].  Batch mode adds the per-column forms [B, 1]
+    (isotropic), [B, N] and [B, N, NFourier]; a 1-D [B] array is taken as per-column isotropic values.  A shape
+    that could be read either way (B == N, or (B, N) == (N, NFourier)) is rejected instead of guessed."""
     t = T(b)
-    if t.numel() == 0 or bool((t == 0).all()):
+    if is_zero is None:
+        is_zero = not _host_any_nonzero(b) if not (isinstance(b, torch.Tensor) and b.is_cuda) else t.numel() == 0
+    if t.numel() == 0 or is_zero:
         return torch.zeros((B, 1, N), dtype=_F64, device=t.device)
     which = "bottom" if name == "b_pos" else "top"
     err = ValueError(f"The shape of the {which} boundary condition is incorrect.")
     if t.numel() == 1 and t.ndim <= 1:
         return t.reshape(1, 1, 1).expand(B, 1, N).contiguous()
     if batched:
+        amb = ValueError(f"`{name}` of shape {tuple(t.shape)} is ambiguous for a batch of {B} columns with "
+                         f"{N} streams per hemisphere: pass per-column values as [B, 1], [B, N] or [B, N, NFourier].")
         if t.ndim == 1 and t.shape[0] == B:
+            if B == N:
+                raise amb
             return t[:, None, None].expand(B, 1, N).contiguous()
         if t.ndim == 2 and t.shape == (B, 1):
             return t[:, :, None].expand(B, 1, N).contiguous()
         if t.ndim == 2 and t.shape == (B, N):
+            if (B, N) == (N, NF):
+                raise amb
             return t[:, None, :].contiguous()
         if t.ndim == 3 and t.shape == (B, N, NF):
             return t.transpose(1, 2).contiguous()
@@ -338,6 +375,64 @@ def _bc_tensor(b, name, B, N, NF, batched, T):
     if t.ndim == 2 and t.shape == (N, NF):
         return t.t()[None].expand(B, NF, N).contiguous()
     raise err
+
+
+# Which inputs of a batched call carry the leading column axis is decided from each argument's RANK (the unbatched
+# rank is fixed by the reference's signature), never from "shape[0] happens to equal B".
+POSITIONAL = ("tau_arr", "omega_arr", "NQuad", "Leg_coeffs_all", "mu0", "I0", "phi0")
+_UNBATCHED_NDIM = {"tau_arr": 1, "omega_arr": 1, "Leg_coeffs_all": 2, "f_arr": 1, "s_poly_coeffs": 2,
+                   "mu0": 0, "I0": 0, "phi0": 0}
+
+
+def _is_array(x):
+    return isinstance(x, (np.ndarray, torch.Tensor))
+
+
+def carries_batch_axis(name, x, B, N=None, NF=None):
+    """True if input `name` of a batched call (B columns) has the leading column axis."""
+    if name == "BDRF_mode":
+        return _is_array(x) and x.ndim == 1 and x.shape[0] == B
+    if not _is_array(x):
+        return False
+    if name in _UNBATCHED_NDIM:
+        return x.ndim == _UNBATCHED_NDIM[name] + 1 and x.shape[0] == B
+    if name in ("b_pos", "b_neg"):  # same reading order as _bc_tensor (which rejects the ambiguous shapes)
+        if x.numel() if isinstance(x, torch.Tensor) else x.size:
+            if x.ndim == 3:
+                return x.shape[0] == B
+            if x.ndim == 2:
+                return tuple(x.shape) in ((B, 1), (B, N))
+            if x.ndim == 1:
+                return x.shape[0] == B and B != 1
+    return False
+
+
+def slice_columns(args, kwargs, lo, hi, B=None):
+    """Columns [lo, hi) of a batched pydisort() call: every input that carries the column axis is sliced, shared
+    inputs are passed through.  Used by the ensemble pipeline and by parallel.shard_inputs."""
+    tau = args[0]
+    if not (_is_array(tau) and tau.ndim == 2):
+        raise ValueError("slice_columns needs a batched call: `tau_arr` must be [B, NLayers].")
+    if B is None:
+        B = tau.shape[0]
+    NQuad = int(args[2])
+    N = NQuad // 2
+    NF = 1 if kwargs.get("only_flux") else int(kwargs.get("NFourier") or NQuad)
+
+    def cut(name, x):
+        return x[lo:hi] if carries_batch_axis(name, x, B, N, NF) else x
+
+    def cut_mode(m):
+        if isinstance(m, TabulatedBDRF) and m.q0 is not None and _is_array(m.q0) and m.q0.ndim == 2 and \
+                m.q0.shape[1] == B and B > 1:
+            return TabulatedBDRF(m.q, m.q0[:, lo:hi])
+        return cut("BDRF_mode", m)
+
+    out_args = tuple(cut(n, a) for n, a in zip(POSITIONAL, args))
+    out_kw = {}
+    for k, v in kwargs.items():
+        out_kw[k] = [cut_mode(m) for m in v] if k == "BDRF_Fourier_modes" else cut(k, v)
+    return out_args, out_kw
 
 
 def _bdrf_tables(modes, B, N, mu_pos, mu0_t, beam, batched, T):
@@ -397,6 +492,8 @@ def pydisort(
     use_banded_solver_NLayers=10,
     autograd_compatible=False,
     _kernel_flags=0,
+    _defer=None,
+    _hints=None,
 ):
     """Solve the 1-D RTE for a column or a batch of columns on the GPU.
 
@@ -406,7 +503,13 @@ def pydisort(
     ``(mu_arr, flux_up, flux_down, u0)`` plus ``u`` unless ``only_flux``.
     ``use_banded_solver_NLayers`` is accepted and validated but unused (one
     block solver covers both of the reference's LAPACK paths).  ``_kernel_flags`` is a test hook: extra
-    ``pd_config.flags`` bits (``_lib.PD_FLAG_GENERIC_KERNELS`` runs the size-generic kernels)."""
+    ``pd_config.flags`` bits (``_lib.PD_FLAG_GENERIC_KERNELS`` runs the size-generic kernels).
+
+    Host synchronisation: inputs that live on the host are inspected on the host; device tensors are never read
+    back to decide anything (a device ``f_arr`` / ``s_poly_coeffs`` / ``I0`` is taken as "may be non-zero", which
+    the kernels resolve per column).  The value checks of pydisort.py:223-291 run in the prologue kernel and are
+    read back once, after the solve kernels have been enqueued; ``ensemble.solve_ensemble`` defers even that to the
+    end of its pipeline (``_defer`` / ``_hints`` are its private hooks)."""
     if autograd_compatible:
         raise NotImplementedError("autograd_compatible=True is not supported by the CUDA implementation.")
     lib, dev = _backend()
@@ -416,7 +519,10 @@ def pydisort(
     def T(x):
         if isinstance(x, torch.Tensor):
             return x.to(device=dev, dtype=_F64, non_blocking=True)
-        return torch.as_tensor(np.asarray(x, dtype=np.float64)).to(dev, non_blocking=True)
+        a = np.asarray(x, dtype=np.float64)
+        if a.size == 1:  # a fill kernel, not a host->device copy (which would queue behind any large upload in flight)
+            return torch.full(a.shape, float(a.reshape(-1)[0]), dtype=_F64, device=dev)
+        return torch.as_tensor(a).to(dev, non_blocking=True)
 
     # ---- shapes (pydisort.py:184-217) ------------------------------------------
     tau = T(tau_arr)
@@ -463,10 +569,11 @@ def pydisort(
                     "of layers which is deduced from the length of `tau_arr`.")
     NLeg_all = leg.shape[-1]
 
+    hints = _hints or {}
     f_t = T(f_arr)
     if f_t.ndim == 0:
         f_t = f_t[None]
-    f_nonzero = bool((f_t != 0).any())
+    f_nonzero = hints["f_nonzero"] if "f_nonzero" in hints else _host_any_nonzero(f_arr)
     if f_nonzero:
         f = per_layer(f_t, (), "The length of `f_arr` does not match the number of layers which is deduced from the "
                       "length of `tau_arr`.")
@@ -476,7 +583,8 @@ def pydisort(
     s_t = T(s_poly_coeffs)
     if s_t.ndim == 1:
         s_t = s_t[None, :]
-    Ns = 0 if (s_t.numel() == 0 or bool((s_t == 0).all())) else int(s_t.shape[-1])
+    s_nonzero = hints["s_nonzero"] if "s_nonzero" in hints else _host_any_nonzero(s_poly_coeffs)
+    Ns = 0 if (s_t.numel() == 0 or not s_nonzero) else int(s_t.shape[-1])
     if Ns > 0:
         s_poly = per_layer(s_t, (None,), "The zeroth dimension of the shape of `s_poly_coeffs` does not match the "
                            "number of layers which is deduced from the length of `tau_arr`.")
@@ -514,15 +622,15 @@ def pydisort(
         raise ValueError("There should be more streams than the number of phase function Legendre coefficients used.")
     if not use_banded_solver_NLayers >= 3:
         raise ValueError("The minimum threshold `use_banded_solver_NLayers` is 3, else the matrix will not be banded.")
-    bpos = _bc_tensor(b_pos, "b_pos", B, N, NFourier, batched, T)
-    bneg = _bc_tensor(b_neg, "b_neg", B, N, NFourier, batched, T)
+    bpos = _bc_tensor(b_pos, "b_pos", B, N, NFourier, batched, T, hints.get("b_pos_zero"))
+    bneg = _bc_tensor(b_neg, "b_neg", B, N, NFourier, batched, T, hints.get("b_neg_zero"))
     NFb = max(bpos.shape[1], bneg.shape[1])
     if bpos.shape[1] != NFb:
         bpos = torch.cat([bpos, torch.zeros((B, NFb - 1, N), dtype=_F64, device=dev)], dim=1)
     if bneg.shape[1] != NFb:
         bneg = torch.cat([bneg, torch.zeros((B, NFb - 1, N), dtype=_F64, device=dev)], dim=1)
 
-    beam = bool((I0_t > 0).any())
+    beam = hints["beam"] if "beam" in hints else _host_any_nonzero(I0)
     nt_static = bool(NT_cor) and not only_flux and NLeg < NLeg_all and f is not None
     mu_h, W_h, mu_d, w_d, ptab = _constants(NQuad, NLeg, NFourier, dev)
 
@@ -544,6 +652,7 @@ def pydisort(
     sol.lib, sol.dev, sol.cfg = lib, dev, cfg
     sol.B, sol.L, sol.N, sol.NQuad, sol.NF = B, L, N, NQuad, NFourier
     sol.batched, sol.want_torch = batched, want_torch
+    sol.defer, sol.pending, sol._tau_max = _defer, [], None
     sol.tau_arr_in = tau_arr
     sol.tau = tau.contiguous()
     sol.omega = omega.contiguous()
@@ -571,7 +680,6 @@ def pydisort(
                          _ptr(sol.colp), _ptr(bpos_s), _ptr(bneg_s), _ptr(pmu0), _ptr(checks), stream)
     sol._check(rc, "pd_prologue")
     _mark("prologue", dev)
-    _raise_for_checks(int(checks.item()))
 
     sol.K = new(B, NFourier, L, N)
     sol.G = new(B, NFourier, L, 2, N, N)
@@ -590,10 +698,50 @@ def pydisort(
     _mark("solve_eigen", dev)
     sol._check(lib.pd_solve_stages(ctypes.byref(cfg), 2, *solve_args), "pd_solve (boundary-condition stage)")
     _mark("solve_bc", dev)
-    bad = int(status.max().item())
     del workspace
+    sol.status = status
+    sol.nt = nt_static
+    # one read-back for the input checks and the per-column status, after everything has been enqueued
+    sol._note("checks", checks)
+    sol._note("status", status)
+    if _defer is None:
+        sol.raise_pending()
+
+    mu_arr = np.concatenate([mu_h, -mu_h])
+    if want_torch:
+        mu_arr = torch.as_tensor(mu_arr, dtype=_F64, device=dev)
+    outs = _make_functions(sol)
+    return (mu_arr,) + (outs[:3] if only_flux else outs)
+
+
+def _host_any_nonzero(x):
+    """Decide a structural flag from host data; a device tensor is never read back (-> "may be non-zero")."""
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            return x.numel() > 0
+        return bool(torch.count_nonzero(x).item())
+    a = np.asarray(x)
+    return bool(a.size) and bool(np.any(a != 0))
+
+
+def _raise_for_pending(pending):
+    """Evaluate queued device-side checks with ONE device->host copy and raise / warn like the reference."""
+    flat = torch.stack([f.reshape(-1).max().to(torch.int64) if f.numel() else torch.zeros((), dtype=torch.int64,
+                                                                                           device=f.device)
+                        for _, f in pending]).cpu().tolist()
+    chk = bad = 0
+    tau_range = False
+    for (kind, f), v in zip(pending, flat):
+        if kind == "checks":
+            chk |= int(v)
+        elif kind == "status":
+            bad |= int(v)
+        elif kind == "tau_range":
+            tau_range = tau_range or bool(v)
+    _raise_for_checks(chk)
     if bad:
-        nbad = int((status != 0).sum().item())
+        nbad = sum(int((f != 0).sum().item()) for kind, f in pending if kind == "status")
+        ncol = sum(f.numel() for kind, f in pending if kind == "status")
         msg = []
         if bad & _lib.PD_ST_QR_NOCONV:
             msg.append("the shifted-QR eigen-solver did not converge")
@@ -601,15 +749,9 @@ def pydisort(
             msg.append("a reduced eigenvalue k^2 was not positive (the reference would return NaN here)")
         if bad & _lib.PD_ST_ZERO_PIVOT:
             msg.append("an exactly singular pivot was met")
-        warnings.warn(f"pydisort_b200: numerical trouble in {nbad} of {B} columns: " + "; ".join(msg) + ".")
-    sol.status = status
-    sol.nt = nt_static
-
-    mu_arr = np.concatenate([mu_h, -mu_h])
-    if want_torch:
-        mu_arr = torch.as_tensor(mu_arr, dtype=_F64, device=dev)
-    outs = _make_functions(sol)
-    return (mu_arr,) + (outs[:3] if only_flux else outs)
+        warnings.warn(f"pydisort_b200: numerical trouble in {nbad} of {ncol} columns: " + "; ".join(msg) + ".")
+    if tau_range:
+        raise ValueError("tau input outside the tau range given for the atmosphere (check `tau_arr`).")
 
 
 def _raise_for_checks(chk):

@@ -22,13 +22,21 @@ __global__ void k_stage_b(PdStageB a, double* hist, long hist_doubles, int sys_d
     }
 }
 
+// Lanes per system: every N x N product needs N^2 operands per lane from other lanes (shared memory), however the
+// columns are dealt out; with two columns per lane each operand feeds two FMAs, which is what the shared-memory
+// pipe (one 128-byte wavefront per cycle per SM against two warp-wide DFMAs) needs to stay off the critical path.
+// N = 16 keeps one column per lane (two would spill).
+#ifndef PD_ADD_LS
+#define PD_ADD_LS(N) ((N) == 16 ? 16 : (N) / 2)
+#endif
 template <int N>
 struct AddCfg {
-    static constexpr int LS = N;                         // lanes per system
+    static constexpr int LS = PD_ADD_LS(N);              // lanes per system
     static constexpr int THREADS = 64;                   // two warps per CTA
     static constexpr int SPC = THREADS / LS;             // systems per CTA
-    static constexpr int MINB = (N <= 4) ? 8 : (N == 8) ? 5 : 3;  // resident CTAs per SM the kernel is compiled for
-    static constexpr size_t SMEM = (size_t)PdStageBAdd<N>::SD * 8 * SPC;
+    static constexpr int MINB = (N == 2) ? 8 : (N == 4) ? 6 : 4;  // resident CTAs per SM the kernel is compiled for
+    using F = PdStageBAdd<N, LS>;
+    static constexpr size_t SMEM = (size_t)F::SD * 8 * SPC;
 };
 
 template <int N>
@@ -39,7 +47,7 @@ __global__ void __launch_bounds__(AddCfg<N>::THREADS, AddCfg<N>::MINB) k_stage_b
     const long slot = (long)blockIdx.x * Cf::SPC + gi;
     const long nslots = (long)gridDim.x * Cf::SPC;
     SubWarp<Cf::LS> g;
-    double* sm = smem + (long)gi * PdStageBAdd<N>::SD;
+    double* sm = smem + (long)gi * Cf::F::SD;
     double* h = hist + slot * hist_doubles;
     const long nsys = (long)a.B * a.NF;
     for (long s = slot; s < nsys; s += nslots) {
@@ -62,7 +70,7 @@ static void plan_add(StageBPlan& p, long nsys, int L) {
     p.add = 1;
     p.add_blocks = (int)blocks;
     p.add_slots = blocks * Cf::SPC;
-    p.add_hist = (long)L * PdStageBAdd<N>::HIST_PER_LAYER;
+    p.add_hist = (long)L * Cf::F::HIST_PER_LAYER;
 }
 
 template <int N>

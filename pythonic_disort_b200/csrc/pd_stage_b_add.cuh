@@ -31,20 +31,24 @@
 #pragma once
 #include "pd_stage_b.cuh"
 
-template <int N>
+template <int N, int LS = 1>
 struct PdStageBAdd {
     static_assert(N >= 2 && N % 2 == 0, "N must be even");
     static constexpr int N2 = 2 * N, NN = N * N;
     static constexpr int LAYER = 2 * NN + N + N2;          // one staged layer: G blocks [2][N][N], k [N], beam vector [2N]
-    static constexpr int NVEC = 8;
-    static constexpr int OFF_RING = 0;                     // [2][LAYER]
-    static constexpr int OFF_VC = OFF_RING + 2 * LAYER;    // V^ column-major; later the columns of R^ (or of R^_s)
+    static constexpr int NVEC = 6;
+    static constexpr int OFF_RING = 0;                     // [LAYER]: the layer in use; the next one is fetched into the
+                                                           // same place as soon as this one has been unpacked
+    static constexpr int OFF_VC = OFF_RING + LAYER;        // V^ column-major; later the columns of R^ (or of R^_s)
     static constexpr int OFF_UC = OFF_VC + NN;             // U^ column-major; later the columns of T^
     static constexpr int OFF_WC = OFF_UC + NN;             // columns of Rup
     static constexpr int OFF_CB = OFF_WC + NN;             // [2][2N] pivot columns (double buffered)
     static constexpr int OFF_VEC = OFF_CB + 4 * N;         // [NVEC][N] vectors every lane needs
     static constexpr int RAW = OFF_VEC + NVEC * N;
-    static constexpr int SD = ((RAW + 15) & ~15) + 2;      // = 2 (mod 16): the systems of a warp broadcast from distinct banks
+    // stride between the systems of a warp = LS (mod 16) doubles: a 128-bit broadcast read serves a quarter warp
+    // (8 / LS systems), a 64-bit per-lane access a half warp (16 / LS systems of LS consecutive doubles each); both
+    // then touch every bank once
+    static constexpr int SD = ((RAW + 15) & ~15) + ((LS < 2 ? 2 : LS) % 16);
     static constexpr long HIST_PER_LAYER = 2 * NN + N2;    // Q^T, (Rup Q)^T, q, Rup q + S
 };
 
@@ -96,7 +100,7 @@ PD_HD double pd_add_gj_solve(const Grp& g, int lane, double (&Mc)[N / Grp::size]
 
 template <class Grp, int N>
 PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double* sm, double* hist) {
-    using F = PdStageBAdd<N>;
+    using F = PdStageBAdd<N, Grp::size>;
     constexpr int LS = Grp::size, NJ = N / LS, N2 = 2 * N, NN = N * N;
     static_assert(N % LS == 0, "lanes per system must divide N");
     const int lane = g.lane();
@@ -126,9 +130,9 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
     const double rmu0 = beam ? 1.0 / mu0 : 0.0;
     bool bad = false;
 
-    // layer ll (G blocks, k, beam vector) -> ring slot ll & 1
+    // layer ll (G blocks, k, beam vector) -> the staging block (asynchronously on the GPU)
     auto stage = [&](int ll) {
-        double* dst = ring + (ll & 1) * F::LAYER;
+        double* dst = ring;
         const double* gs = Gc + (long)ll * 2 * NN;
         const double* ks = Kc + (long)ll * N;
 #if defined(__CUDA_ARCH__)
@@ -199,16 +203,16 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
         }
     };
     // particular solution of layer l (hat basis) at the top (tau*_l, attenuation at) and bottom (tau*_{l+1}, ab)
-    auto particular = [&](int l, const double* Bl, double at, double ab, double (&ptp)[NJ], double (&ptm)[NJ],
-                          double (&pbp)[NJ], double (&pbm)[NJ]) {
+    auto particular = [&](int l, const double (&blp)[NJ], const double (&blm)[NJ], double at, double ab,
+                          double (&ptp)[NJ], double (&ptm)[NJ], double (&pbp)[NJ], double (&pbm)[NJ]) {
 #pragma unroll
         PD_FOR_OWN(ii, i) {
             double a = 0.0, c = 0.0, d = 0.0, e = 0.0;
             if (beam) {
-                a = Bl[i] * at;
-                c = Bl[N + i] * at;
-                d = Bl[i] * ab;
-                e = Bl[N + i] * ab;
+                a = blp[ii] * at;
+                c = blm[ii] * at;
+                d = blp[ii] * ab;
+                e = blm[ii] * ab;
             }
             if (dthc) {
                 const double* dl = dthc + (long)l * A.Ns * N2;
@@ -239,14 +243,13 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
     double att_t = 1.0;  // exp(-tau*_l / mu0), tau*_0 = 0
     for (int l = 0; l < L; ++l) {
         stage_wait();
-        if (l + 1 < L) stage(l + 1);
-        const double* Gl = ring + (l & 1) * F::LAYER;
+        const double* Gl = ring;
         const double* Kl = Gl + 2 * NN;
         const double* Bl = Kl + N;
         const double dtau = taus[l + 1] - taus[l];
         const double att_b = beam ? exp(-taus[l + 1] * rmu0) : 0.0;
 
-        double Rh[NJ][N], Th[NJ][N];
+        double Rh[NJ][N], Th[NJ][N], blp[NJ], blm[NJ];
         {
             double vrow[NJ][N], urow[NJ][N];
             eigvec_columns(Gl, vrow, urow);
@@ -266,8 +269,11 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
                 const double dk = (em / (2.0 + em)) / gk;
                 bad = bad || !(gk < 0.0) || !(dk >= 0.0);
                 vec[k] = dk;
+                blp[kk] = beam ? Bl[k] : 0.0;
+                blm[kk] = beam ? Bl[N + k] : 0.0;
             }
             g.sync();
+            if (l + 1 < L) stage(l + 1);  // the staged copy of layer l is used up: fetch the next one behind the arithmetic
             // columns j of I + U^ d U^T and I + V^ d V^T
             double X1[NJ][N], X2[NJ][N];
 #pragma unroll
@@ -337,7 +343,7 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
         }
         // source terms
         double ptp[NJ], ptm[NJ], pbp[NJ], pbm[NJ];
-        particular(l, Bl, att_t, att_b, ptp, ptm, pbp, pbm);
+        particular(l, blp, blm, att_t, att_b, ptp, ptm, pbp, pbm);
 #pragma unroll
         PD_FOR_OWN(ii, i) {
             vec[N + i] = ptm[ii];
@@ -470,19 +476,16 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
         }
     };
     load_history(L - 1);
-    double att_b = att_t;  // exp(-tau*_L / mu0)
+    double att_b = att_t;  // exp(-tau*_L / mu0); the staging block still holds layer L - 1
     for (int l = L - 1; l >= 0; --l) {
-        if (l != L - 1) stage_wait();
-        else g.sync();
-        if (l > 0) stage(l - 1);
-        const double* Gl = ring + (l & 1) * F::LAYER;
-        const double* Kl = Gl + 2 * NN;
-        const double* Bl = Kl + N;
         const double dtau = taus[l + 1] - taus[l];
         const double at = beam ? exp(-taus[l] * rmu0) : 0.0;
 #pragma unroll
         PD_FOR_OWN(ii, i) vec[i] = ubp[ii];
-        g.sync();
+        stage_wait();
+        const double* Gl = ring;
+        const double* Kl = Gl + 2 * NN;
+        const double* Bl = Kl + N;
         double utp[NJ], utm[NJ];
 #pragma unroll
         PD_FOR_OWN(ii, i) {
@@ -490,10 +493,18 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
             utm[ii] = rsi[ii] + dot_own(RQr[ii], vec);
         }
         if (l > 0) load_history(l - 1);  // in flight while this layer's coefficients are recovered
-        double vrow[NJ][N], urow[NJ][N];
+        double vrow[NJ][N], urow[NJ][N], blp[NJ], blm[NJ], El[NJ];
         eigvec_columns(Gl, vrow, urow);
+#pragma unroll
+        PD_FOR_OWN(kk, k) {
+            blp[kk] = beam ? Bl[k] : 0.0;
+            blm[kk] = beam ? Bl[N + k] : 0.0;
+            El[kk] = exp(-Kl[k] * dtau);
+        }
+        g.sync();
+        if (l > 0) stage(l - 1);
         double ptp[NJ], ptm[NJ], pbp[NJ], pbm[NJ];
-        particular(l, Bl, at, att_b, ptp, ptm, pbp, pbm);
+        particular(l, blp, blm, at, att_b, ptp, ptm, pbp, pbm);
 #pragma unroll
         PD_FOR_OWN(ii, i) {
             const double htp = utp[ii] - ptp[ii], htm = utm[ii] - ptm[ii];
@@ -518,8 +529,7 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
                 t0 = fma(v2.x, ds.x, t0);
                 t1 = fma(v2.y, ds.y, t1);
             }
-            const double E = exp(-Kl[k] * dtau);
-            const double sc = 0.25 / ((g0 + g1) * (1.0 + E));  // (1 / (2 g (1 + E))) / 2
+            const double sc = 0.25 / ((g0 + g1) * (1.0 + El[kk]));  // (1 / (2 g (1 + E))) / 2
             const double ss = (s0 + s1) * sc, tt = (t0 + t1) * sc;
             Cout[(long)l * N2 + k] = ss + tt;
             Cout[(long)l * N2 + N + k] = ss - tt;
