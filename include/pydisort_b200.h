@@ -28,6 +28,8 @@ extern "C" {
 #endif
 
 #define PD_ABI_VERSION 1
+#define PD_MAX_NQUAD 92   /* largest NQuad: one system's elimination panel (size-generic stage B) must fit one CTA's
+                           * 227 KB of shared memory; larger values are rejected by every entry point (-8)        */
 
 /* pd_config.flags */
 #define PD_FLAG_BEAM      (1 << 0) /* there_is_beam_source  (pydisort.py:215)            */

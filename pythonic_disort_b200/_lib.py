@@ -34,6 +34,7 @@ class pd_state(ctypes.Structure):
 PD_FLAG_BEAM, PD_FLAG_ISO, PD_FLAG_DELTA_M, PD_FLAG_BDRF_PERCOL, PD_FLAG_GENERIC_KERNELS = 1, 2, 4, 8, 256
 PD_ST_QR_NOCONV, PD_ST_BAD_EIGEN, PD_ST_ZERO_PIVOT = 1, 2, 4
 PD_NCOLP = 8
+PD_MAX_NQUAD = 92
 PD_COL_MU0, PD_COL_I0, PD_COL_RESCALE, PD_COL_PHI0, PD_COL_I0_RAW, PD_COL_DM, PD_COL_NT = 0, 1, 2, 3, 4, 5, 6
 CHK = dict(TAU_POS=1 << 0, THICK_POS=1 << 1, OMEGA_RANGE=1 << 2, LEG_RANGE=1 << 3, I0_NEG=1 << 4, MU0_RANGE=1 << 5,
            PHI0_RANGE=1 << 6, F_RANGE=1 << 7, LEG0_FIXED=1 << 8, OMEGA_NEAR1=1 << 9, LEG_NEAR1=1 << 10,

@@ -610,6 +610,9 @@ def pydisort(
         raise ValueError("There must be at least two streams.")
     if not NQuad % 2 == 0:
         raise ValueError("The number of streams must be even.")
+    if NQuad > _lib.PD_MAX_NQUAD:
+        raise ValueError(f"NQuad = {NQuad} is not supported by the CUDA kernels: at most {_lib.PD_MAX_NQUAD} streams "
+                         "(one system's elimination panel has to fit the shared memory of one SM).")
     if not NFourier > 0:
         raise ValueError("The number of Fourier modes to use in the solution must be positive.")
     if not NFourier <= NLeg:
@@ -719,13 +722,19 @@ def _host_any_nonzero(x):
     if isinstance(x, torch.Tensor):
         if x.is_cuda:
             return x.numel() > 0
-        return bool(torch.count_nonzero(x).item())
+        x = x.detach().numpy()
     a = np.asarray(x)
-    return bool(a.size) and bool(np.any(a != 0))
+    if a.size == 0:
+        return False
+    if a.size > 4096 and np.any(a.reshape(-1)[:4096] != 0):  # the usual case for a gigabyte-sized input: no full pass
+        return True
+    return bool(np.any(a != 0))
 
 
 def _raise_for_pending(pending):
     """Evaluate queued device-side checks with ONE device->host copy and raise / warn like the reference."""
+    if not pending:
+        return
     flat = torch.stack([f.reshape(-1).max().to(torch.int64) if f.numel() else torch.zeros((), dtype=torch.int64,
                                                                                            device=f.device)
                         for _, f in pending]).cpu().tolist()

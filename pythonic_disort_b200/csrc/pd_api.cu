@@ -31,7 +31,7 @@ int pd_check_cfg(const pd_config* c) {
     if (c->NFourier < 1 || c->NFourier > c->NLeg) return -5;
     if (c->NBDRF < 0 || c->Nscoeffs < 0) return -6;
     if (c->NFb != 1 && c->NFb != c->NFourier) return -7;
-    if (c->NQuad > 128) return -8;
+    if (c->NQuad > PD_MAX_NQUAD) return -8;
     return 0;
 }
 

@@ -25,16 +25,17 @@ __global__ void k_stage_b(PdStageB a, double* hist, long hist_doubles, int sys_d
 // Lanes per system: every N x N product needs N^2 operands per lane from other lanes (shared memory), however the
 // columns are dealt out; with two columns per lane each operand feeds two FMAs, which is what the shared-memory
 // pipe (one 128-byte wavefront per cycle per SM against two warp-wide DFMAs) needs to stay off the critical path.
-// N = 16 keeps one column per lane (two would spill).
+// N = 16 keeps one column per lane (two would spill); for N = 4 the per-lane transcendental and control overhead,
+// which doubles with two columns per lane, outweighs the products (measured: 56 against 43 ms per 1M LW columns).
 #ifndef PD_ADD_LS
-#define PD_ADD_LS(N) ((N) == 16 ? 16 : (N) / 2)
+#define PD_ADD_LS(N) ((N) == 8 ? 4 : (N))
 #endif
 template <int N>
 struct AddCfg {
     static constexpr int LS = PD_ADD_LS(N);              // lanes per system
     static constexpr int THREADS = 64;                   // two warps per CTA
     static constexpr int SPC = THREADS / LS;             // systems per CTA
-    static constexpr int MINB = (N == 2) ? 8 : (N == 4) ? 6 : 4;  // resident CTAs per SM the kernel is compiled for
+    static constexpr int MINB = (N <= 4) ? 8 : 4;  // resident CTAs per SM the kernel is compiled for
     using F = PdStageBAdd<N, LS>;
     static constexpr size_t SMEM = (size_t)F::SD * 8 * SPC;
 };

@@ -17,6 +17,7 @@ and with it the next chunk's launches, for the length of that copy -- which is w
 NumPy / pageable inputs go through the driver's staging copy (correct, but not overlapped).  Results land in pinned
 host tensors (``out=`` lets a caller recycle them) and are returned as NumPy views.
 """
+import contextlib
 import warnings
 
 import numpy as np
@@ -35,6 +36,16 @@ def _copy_streams(dev):
     return _streams[key]
 
 
+class _NoStream:
+    """Stand-in for streams / events when the backend has none (the CPU test-suite drives the same chunking and
+    assembly logic through the host build of the kernels; the product always runs on CUDA)."""
+
+    def wait_stream(self, *a): pass
+    def wait_event(self, *a): pass
+    def record(self, *a): pass
+    def synchronize(self): pass
+
+
 def pinned(x):
     """A pinned (page-locked) host copy of ``x`` as a torch tensor: the input form ``solve_ensemble`` can copy
     asynchronously.  Arrays that are already pinned tensors are returned as they are."""
@@ -44,14 +55,20 @@ def pinned(x):
 
 
 def default_chunk(B, L, NQuad, NFourier):
-    """Columns per pydisort() call: solved state of a chunk (K, G, Bv, C) around 12 GB, a multiple of 1024, and
-    at least six chunks per ensemble so that the first upload and the last download are small next to the rest."""
+    """Columns per pydisort() call: solved state of a chunk (K, G, Bv, C) below ~24 GB, a multiple of 1024 (one that
+    divides B if there is one), and at least six chunks per ensemble so that the first upload and the last download
+    are small next to the rest."""
     N = NQuad // 2
     per_col = NFourier * L * (2 * N * N + 5 * N) * 8
-    chunk = max(1024, int(12e9 / per_col) // 1024 * 1024)
+    limit = max(1024, min(int(24e9 / per_col), 1 << 17) // 1024 * 1024)
     if B >= 6 * 1024:
-        chunk = min(chunk, max(1024, (B // 6) // 1024 * 1024))
-    return max(1, min(B, chunk, 1 << 17))
+        limit = min(limit, max(1024, (B // 6) // 1024 * 1024))
+    if B <= limit:
+        return max(1, B)
+    for c in range(limit, max(1023, limit // 2), -1024):
+        if B % c == 0:
+            return c
+    return limit
 
 
 class EnsembleResult(dict):
@@ -95,6 +112,7 @@ def solve_ensemble(tau_arr, omega_arr, NQuad, Leg_coeffs_all, mu0, I0, phi0, *, 
     ``wait=False`` returns as soon as everything is enqueued (call ``.wait()`` before reading), which lets
     consecutive ensembles overlap."""
     lib, dev = api._backend()
+    cuda = dev.type == "cuda"
     args = (tau_arr, omega_arr, NQuad, Leg_coeffs_all, mu0, I0, phi0)
     if not (api._is_array(tau_arr) and tau_arr.ndim == 2):
         raise ValueError("solve_ensemble needs a batch of columns: `tau_arr` must be [B, NLayers].")
@@ -142,8 +160,8 @@ def solve_ensemble(tau_arr, omega_arr, NQuad, Leg_coeffs_all, mu0, I0, phi0, *, 
     old = out.tensors if isinstance(out, EnsembleResult) else {}
     for name, shp in shapes.items():
         t = old.get(name)
-        if t is None or tuple(t.shape) != shp or not t.is_pinned():
-            t = torch.empty(shp, dtype=_F64, pin_memory=True)
+        if t is None or tuple(t.shape) != shp or (cuda and not t.is_pinned()):
+            t = torch.empty(shp, dtype=_F64, pin_memory=cuda)
         res.tensors[name] = t
         res[name] = t.numpy()
 
@@ -177,8 +195,15 @@ def solve_ensemble(tau_arr, omega_arr, NQuad, Leg_coeffs_all, mu0, I0, phi0, *, 
         kwargs = dict(kwargs, BDRF_Fourier_modes=tabs)
     kwargs = {k: (v if k == "BDRF_Fourier_modes" else shared_to_device(k, v)) for k, v in kwargs.items()}
 
-    cur = torch.cuda.current_stream(dev)
-    h2d_stream, d2h_stream = _copy_streams(dev)
+    if cuda:
+        cur = torch.cuda.current_stream(dev)
+        h2d_stream, d2h_stream = _copy_streams(dev)
+        on = torch.cuda.stream
+        new_event = torch.cuda.Event
+    else:
+        cur = h2d_stream = d2h_stream = _NoStream()
+        on = lambda s_: contextlib.nullcontext()  # noqa: E731
+        new_event = _NoStream
     h2d_stream.wait_stream(cur)   # inputs prepared on the caller's stream (if any) are complete before we read them
     moved = [0]
 
@@ -187,6 +212,8 @@ def solve_ensemble(tau_arr, omega_arr, NQuad, Leg_coeffs_all, mu0, I0, phi0, *, 
             x = torch.from_numpy(np.ascontiguousarray(x))
         if isinstance(x, torch.Tensor) and not x.is_cuda:
             moved[0] += x.numel() * x.element_size()
+            if not cuda:
+                return x
             d = x.to(dev, non_blocking=True)
             d.record_stream(cur)
             return d
@@ -194,12 +221,12 @@ def solve_ensemble(tau_arr, omega_arr, NQuad, Leg_coeffs_all, mu0, I0, phi0, *, 
 
     def stage(lo, hi):
         ca, ck = api.slice_columns(args, kwargs, lo, hi, B)
-        with torch.cuda.stream(h2d_stream):
+        with on(h2d_stream):
             ca = tuple(up(a) for a in ca)
             ck = {k: ([up(m) if api._is_array(m) else m for m in v] if k == "BDRF_Fourier_modes" else up(v))
                   for k, v in ck.items()}
             tq = up(tau_q[lo:hi] if tau_batched else tau_q)
-            ev = torch.cuda.Event()
+            ev = new_event()
             ev.record(h2d_stream)
         return ca, ck, tq, ev
 
@@ -223,18 +250,19 @@ def solve_ensemble(tau_arr, omega_arr, NQuad, Leg_coeffs_all, mu0, I0, phi0, *, 
                 got["u0"] = sol[3](tq) if mu is None else sol[3].at_mu(mu, tq)
             if "u" in want:
                 got["u"] = sol[4](tq, phi_d) if mu is None else sol[4].at_mu(mu, tq, phi_d)
-            done = torch.cuda.Event()
+            done = new_event()
             done.record(cur)
-            with torch.cuda.stream(d2h_stream):
+            with on(d2h_stream):
                 d2h_stream.wait_event(done)
                 for name, t in got.items():
-                    t = t.reshape((hi - lo,) + tuple(res.tensors[name].shape[1:]))
-                    t.record_stream(d2h_stream)
+                    t = torch.as_tensor(t).reshape((hi - lo,) + tuple(res.tensors[name].shape[1:]))
+                    if cuda:
+                        t.record_stream(d2h_stream)
                     res.tensors[name][lo:hi].copy_(t, non_blocking=True)
                     res.d2h_bytes += t.numel() * 8
             del sol, got
     res.h2d_bytes = moved[0]
     res.chunks = len(starts)
-    res._done = torch.cuda.Event()
+    res._done = new_event()
     res._done.record(d2h_stream)
     return res.wait() if wait else res

@@ -284,8 +284,46 @@ def run_hapke():
     print("hapke modes:", modes.shape)
 
 
+def run_actinic():
+    """Row a13: the reference's actinic-flux functions (``generate_diff_act_flux_funcs``, subroutines.py:258-318, on
+    the ``u0`` of ``_assemble_intensity_and_fluxes.py:334-433`` with its delta-scaling reclassification term,
+    :360-371) on the level grid of SW columns (delta-M: the reclassification is active), LW columns (thermal,
+    no beam), test problem 9c and a single-layer delta-M problem with its tau-antiderivative."""
+    from pythonic_disort_b200 import synthetic
+    out = {}
+    for name, ncol in (("sw", 3), ("lw", 4), ("tp9c", 1)):
+        ens = synthetic.make(name, ncol)
+        up, dn = [], []
+        for b in range(ncol):
+            args, kwargs = synthetic.column_call(ens, b)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                res = _orig_pydisort(*args, **kwargs)
+            fu, fd = ref_sub.generate_diff_act_flux_funcs(res[3])
+            t = ens["tau_eval"][b]
+            up.append(fu(t))
+            dn.append(fd(t))
+        out[f"{name}_ncol"] = np.array(ncol)
+        out[f"{name}_up"] = np.array(up)
+        out[f"{name}_down"] = np.array(dn)
+        print(f"actinic {name}: {ncol} columns", out[f"{name}_up"].shape)
+    # one layer, delta-M scaled, with the antiderivative (the reference's multi-layer antiderivatives are broken, DESIGN.md)
+    NQuad = 8
+    leg = 0.8 ** np.arange(NQuad + 4)
+    args1 = (np.array([1.7]), np.array([0.9]), NQuad, leg[None, :], 0.6, 2.0, 0.3)
+    kw1 = dict(f_arr=np.array([leg[NQuad]]), NT_cor=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = _orig_pydisort(*args1, **kw1)
+    fu, fd = ref_sub.generate_diff_act_flux_funcs(res[3])
+    t1 = np.linspace(0, 1.7, 9)
+    out.update(one_tau=t1, one_up=fu(t1), one_down=fd(t1), one_up_anti=fu(t1, True), one_down_anti=fd(t1, True),
+               one_leg=leg, one_f=np.array([leg[NQuad]]))
+    np.savez_compressed(os.path.join(HERE, "actinic.npz"), **out)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["suite", "stamnes", "ensembles", "interpolate", "thermal", "hapke"]
+    what = sys.argv[1:] or ["suite", "stamnes", "ensembles", "interpolate", "thermal", "hapke", "actinic"]
     if "suite" in what:
         run_reference_suite()
     if "stamnes" in what:
@@ -298,3 +336,5 @@ if __name__ == "__main__":
         run_thermal()
     if "hapke" in what:
         run_hapke()
+    if "actinic" in what:
+        run_actinic()
