@@ -65,7 +65,10 @@ def group_scale(refs):
     return max(vals) if vals else 0.0
 
 
-def parity(mine, ref, floor=1e-3, scale=None):
+PW_FLOOR = 1e-6  # the pointwise criterion applies where |X_ref| > 1e-6 * max|X_ref|
+
+
+def parity(mine, ref, floor=PW_FLOOR, scale=None):
     """(scale-relative error, worst pointwise relative error over entries with
     |ref| > floor * scale, number of non-finite reference entries masked);
     scale defaults to max|ref|."""
@@ -93,6 +96,38 @@ def conditioning_tolerance(omega, base=1e-9):
     Tolerance: ``base`` up to omega = 0.9999, then growing like 1/(1-omega)."""
     wmax = float(np.max(omega))
     return base * max(1.0, 1e-4 / max(1.0 - wmax, 1e-12))
+
+
+def perturb_inputs(args, kwargs, seed):
+    """The same problem with every floating-point input array moved by one unit in the last place, up or down at random
+    (optical depths, single-scattering albedos, phase-function moments above the zeroth, source polynomials).
+    Used to measure how far the REFERENCE ALGORITHM itself moves under a perturbation no caller can see
+    (``reference_sensitivity``): no re-ordered implementation can be expected to sit closer to the reference's
+    output than that.  The lowest level stays where it is so that recorded query depths remain inside the
+    atmosphere."""
+    rng = np.random.default_rng(seed)
+
+    def p(x):
+        x = np.array(x, dtype=float)
+        up = rng.integers(0, 2, x.shape) > 0
+        return np.nextafter(x, np.where(up, np.inf, -np.inf))
+
+    a = list(args)
+    tau = np.array(a[0], dtype=float)
+    scalar_tau = tau.ndim == 0
+    tau = np.atleast_1d(tau)
+    tp = p(tau)
+    tp[..., -1] = tau[..., -1]
+    a[0] = float(tp[0]) if scalar_tau else tp
+    a[1] = p(a[1]) if np.ndim(a[1]) else float(p(a[1]))
+    leg = np.array(a[3], dtype=float)
+    lp = p(leg)
+    lp[..., 0] = leg[..., 0]
+    a[3] = lp
+    kw = dict(kwargs)
+    if kw.get("s_poly_coeffs") is not None:
+        kw["s_poly_coeffs"] = p(kw["s_poly_coeffs"])
+    return tuple(a), kw
 
 
 def run_calls(outputs, rec):

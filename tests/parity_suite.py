@@ -13,20 +13,74 @@ def to_np(x):
     return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
 
 
+# How many times the reference algorithm's own response to a 1-ulp change of its inputs an implementation may differ
+# from the reference by, before the 1e-9 bars of SURVEY.md 8(c) give way.  Scale criterion: 4 (the omega = 1 - 1e-6
+# test problems: CUDA path 6.6e-9 / oracle 2.5e-9 / 1-ulp response 4.9e-9 on 1b).  Pointwise criterion: 64 -- an entry
+# a million times below the field's maximum that is the cancellation residue of the thermal source polynomial of a
+# micrometre-thin layer (8ARTS_A: s0 + s1 tau with |s1 tau| ~ 1e7 |result|) carries one rounding of the large terms per
+# evaluation and per layer it is carried through; three random 1-ulp draws move it by 1-3 such quanta, two correct
+# implementations differ by a few tens of them (measured: up to 37 on the host build, 28 on the GPU).  In backward-
+# error terms: the result is the reference's for inputs that differ by at most 64 ulp.
+SENS_FACTOR = 4.0
+SENS_FACTOR_PW = 64.0
+SENS_DRAWS = 3
+
+
+def _oracle():
+    from oracle import disort_oracle  # test infrastructure (this module lives under tests/)
+    return disort_oracle.pydisort
+
+
+def record_sensitivity(rec, draws=SENS_DRAWS):
+    """Per recorded call and output: (scale error, pointwise error) by which the reference algorithm (the pinned
+    oracle) moves when its inputs move by one unit in the last place -- the conditioning of the problem as posed,
+    measured, not modelled.  Zero for well-conditioned problems (where the plain 1e-9 bars apply), ~1e-8 for the
+    omega = 1 - 1e-6 test problems, ~1e-5 pointwise where an output entry is the cancellation residue of terms a
+    million times larger (8ARTS_A's micrometre-thin layers)."""
+    oracle = _oracle()
+
+    def evaluate(args, kwargs):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = oracle(*args, **kwargs)
+            return [[np.squeeze(np.asarray(g, dtype=float)) for g in got] for _, got in golden_io.run_calls(out, rec)]
+
+    base = evaluate(rec["args"], rec["kwargs"])
+    sens = [[(0.0, 0.0)] * len(c) for c in base]
+    for d in range(draws):
+        moved = evaluate(*golden_io.perturb_inputs(rec["args"], rec["kwargs"], seed=1000 + d))
+        for ci, call in enumerate(rec["calls"]):
+            scale = golden_io.group_scale(call["outs"])
+            for k in range(len(base[ci])):
+                e, pw, _ = golden_io.parity(moved[ci][k], base[ci][k], scale=scale)
+                sens[ci][k] = (max(sens[ci][k][0], e), max(sens[ci][k][1], pw))
+    return sens
+
+
 def check_suite_record_outputs(pydisort, name, max_records=None, base_tol=1e-9):
-    """Every evaluation the reference test `name` performs, against the reference's own FP64 output."""
+    """Every evaluation the reference test `name` performs, against the reference's own FP64 output, by both
+    criteria of SURVEY.md 8(c): max|X - X_ref| <= 1e-9 max|X_ref| per field, and pointwise
+    |X - X_ref| <= 1e-9 |X_ref| wherever |X_ref| > 1e-6 max|X_ref|.  Where the problem itself is ill-conditioned
+    both bars widen to SENS_FACTOR (scale) / SENS_FACTOR_PW (pointwise) x the reference algorithm's own response to a
+    1-ulp change of its inputs (``record_sensitivity``); the scale criterion additionally never exceeds the analytic omega -> 1 bound of
+    ``golden_io.conditioning_tolerance``."""
     records, _ = golden_io.load_test(name)
     worst = 0.0
     for rec in records[:max_records]:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             out = pydisort(*rec["args"], **rec["kwargs"])
-        tol = golden_io.conditioning_tolerance(rec["args"][1], base_tol)
-        for call, got in golden_io.run_calls(out, rec):
+        cap = golden_io.conditioning_tolerance(rec["args"][1], base_tol)
+        sens = record_sensitivity(rec)
+        for ci, (call, got) in enumerate(golden_io.run_calls(out, rec)):
             scale = golden_io.group_scale(call["outs"])
-            for g, r in zip(got, call["outs"]):
-                err, _, _ = golden_io.parity(np.squeeze(to_np(g)), np.squeeze(r), scale=scale)
-                assert err <= tol, (name, call["fn"], "anti" if call["anti"] else "", err, tol)
+            for k, (g, r) in enumerate(zip(got, call["outs"])):
+                err, pw, _ = golden_io.parity(np.squeeze(to_np(g)), np.squeeze(r), scale=scale)
+                tol = min(cap, max(base_tol, SENS_FACTOR * sens[ci][k][0]))
+                tol_pw = max(base_tol, SENS_FACTOR_PW * sens[ci][k][1])
+                where = (name, call["fn"], "anti" if call["anti"] else "")
+                assert err <= tol, where + ("scale criterion", err, tol)
+                assert pw <= tol_pw, where + ("pointwise criterion", pw, tol_pw)
                 worst = max(worst, err / tol)
     return worst
 
@@ -69,26 +123,137 @@ def run_batched(pydisort, ens):
     return res
 
 
-def compare_fields(got, ref, ncol, tol=1e-9, label=""):
-    """Per column and field: max|X - X_ref| <= tol * scale; returns the worst ratio and the
-    worst pointwise-relative error over entries larger than 1e-3 of the field's scale."""
+def _field_scale(ref, key, b):
+    if key.startswith("flux"):
+        return golden_io.group_scale([ref[k][b] for k in ("flux_up", "flux_down_diffuse", "flux_down_direct")])
+    return None
+
+
+def compare_fields(got, ref, ncol, tol=1e-9, label="", sens=None, base_tol=1e-9):
+    """Per column and field, both criteria of SURVEY.md 8(c): max|X - X_ref| <= bar * scale, and pointwise
+    |X - X_ref| <= bar_pw * |X_ref| wherever |X_ref| > 1e-6 * scale.  ``tol`` caps the scale bar (the analytic
+    omega -> 1 bound); with ``sens`` (``ensemble_sensitivity``) both bars are 1e-9 unless SENS_FACTOR / SENS_FACTOR_PW
+    times the reference algorithm's own response to a 1-ulp change of this column's inputs is larger.  Without ``sens``
+    (CUDA path against itself) only the scale criterion is asserted.  Returns the worst errors."""
     worst, worst_pw, masked = 0.0, 0.0, 0
     for b in range(ncol):
-        fscale = golden_io.group_scale([ref[k][b] for k in ("flux_up", "flux_down_diffuse", "flux_down_direct")])
         for key in got:
-            scale = fscale if key.startswith("flux") else None
-            err, pw, nmask = golden_io.parity(got[key][b], ref[key][b], scale=scale)
-            assert err <= tol, (label, key, b, err)
+            err, pw, nmask = golden_io.parity(got[key][b], ref[key][b], scale=_field_scale(ref, key, b))
+            bar = tol
+            if sens is not None:
+                bar = min(tol, max(base_tol, SENS_FACTOR * sens[key][b][0]))
+                bar_pw = max(base_tol, SENS_FACTOR_PW * sens[key][b][1])
+                assert pw <= bar_pw, (label, key, b, "pointwise criterion", pw, bar_pw)
+            assert err <= bar, (label, key, b, "scale criterion", err, bar)
             worst, worst_pw, masked = max(worst, err), max(worst_pw, pw), masked + nmask
     return worst, worst_pw, masked
 
 
+def _oracle_job(job):
+    """Oracle on columns [first, first + ncol) of ensemble `name`; `seed` = None for the inputs as they are, else the
+    1-ulp perturbation of golden_io.perturb_inputs.  Top-level so that a process pool can run it."""
+    name, first, ncol, seed = job
+    ens = synthetic.make(name, ncol, first)
+    if seed is not None:
+        a, k = golden_io.perturb_inputs(ens["args"], ens["kwargs"], seed)
+        ens = dict(ens, args=a, kwargs=k)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return synthetic.run_reference_like(_oracle(), ens)
+
+
+def oracle_on_ensemble(name, ncol, first=0, seeds=(None,), pool=None):
+    """[oracle outputs for every seed]; columns are spread over `pool` (a multiprocessing pool) when given."""
+    workers = pool._processes if pool is not None else 1
+    per = max(1, -(-ncol // workers))
+    jobs = [(name, first + lo, min(per, ncol - lo), seed) for seed in seeds for lo in range(0, ncol, per)]
+    parts = pool.map(_oracle_job, jobs) if pool is not None else [_oracle_job(j) for j in jobs]
+    nper = len(jobs) // len(seeds)
+    return [{k: np.concatenate([p[k] for p in parts[i * nper:(i + 1) * nper]]) for k in parts[0]}
+            for i in range(len(seeds))]
+
+
+def ensemble_sensitivity(base, moved):
+    """field -> per column (scale error, pointwise error) of the perturbed oracle runs against the unperturbed one."""
+    sens = {}
+    for key in base:
+        rows = []
+        for b in range(len(base[key])):
+            scale = _field_scale(base, key, b)
+            e = [golden_io.parity(m[key][b], base[key][b], scale=scale)[:2] for m in moved]
+            rows.append((max(x[0] for x in e), max(x[1] for x in e)))
+        sens[key] = rows
+    return sens
+
+
 def check_ensemble_vs_golden(pydisort, name, tol=1e-9):
+    """First columns of a synthetic ensemble against the outputs of the unmodified reference (tests/golden/ensemble_*)."""
     gold = np.load(os.path.join(golden_io.GOLDEN, f"ensemble_{name}.npz"))
     ncol = int(gold["ncol"])
     ens = synthetic.make(name, ncol)
     got = run_batched(pydisort, ens)
-    return compare_fields(got, {k: gold[k] for k in got}, ncol, tol, name)
+    runs = oracle_on_ensemble(name, ncol, 0, seeds=(None,) + tuple(range(2000, 2000 + SENS_DRAWS)))
+    sens = ensemble_sensitivity(runs[0], runs[1:])
+    return compare_fields(got, {k: gold[k] for k in got}, ncol, tol, name, sens=sens)
+
+
+def check_ensemble_vs_live_oracle(pydisort, name, ncol, first, pool=None):
+    """A larger slice (256 SW / 1,024 LW / 64 HA columns) against the pinned oracle run live."""
+    ens = synthetic.make(name, ncol, first)
+    got = run_batched(pydisort, ens)
+    runs = oracle_on_ensemble(name, ncol, first, seeds=(None,) + tuple(range(3000, 3000 + SENS_DRAWS)), pool=pool)
+    sens = ensemble_sensitivity(runs[0], runs[1:])
+    tol = golden_io.conditioning_tolerance(ens["args"][1])
+    return compare_fields(got, runs[0], ncol, tol, name, sens=sens)
+
+
+def check_actinic_vs_golden(pd_module, tol=1e-9):
+    """Row a13: ``generate_diff_act_flux_funcs`` (subroutines.py:258-318) on this package's ``u0`` -- including the
+    delta-scaling reclassification term of ``_assemble_intensity_and_fluxes.py:360-371`` -- against the reference's
+    actinic fluxes on SW columns (delta-M active), LW columns (thermal), test problem 9c and a one-layer delta-M
+    problem with its tau-antiderivative (tests/golden/actinic.npz, made by make_golden.py from the unmodified
+    reference).  Both 8(c) criteria; the upward and downward actinic flux of a column share one scale."""
+    gold = np.load(os.path.join(golden_io.GOLDEN, "actinic.npz"))
+    sub = pd_module.subroutines
+    worst = 0.0
+
+    def compare(got, ref, where):
+        nonlocal worst
+        scale = golden_io.group_scale(ref)
+        for g, r in zip(got, ref):
+            err, pw, _ = golden_io.parity(np.squeeze(to_np(g)), np.squeeze(r), scale=scale)
+            assert err <= tol and pw <= tol, where + (err, pw)
+            worst = max(worst, err)
+
+    for name in ("sw", "lw", "tp9c"):
+        ncol = int(gold[f"{name}_ncol"])
+        ens = synthetic.make(name, ncol)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = pd_module.pydisort(*ens["args"], **ens["kwargs"])
+        up, down = sub.generate_diff_act_flux_funcs(out[3])
+        got_up, got_dn = np.atleast_2d(to_np(up(ens["tau_eval"]))), np.atleast_2d(to_np(down(ens["tau_eval"])))
+        assert got_up.shape == gold[f"{name}_up"].shape
+        for b in range(ncol):
+            compare((got_up[b], got_dn[b]), (gold[f"{name}_up"][b], gold[f"{name}_down"][b]), (name, b))
+            args, kwargs = synthetic.column_call(ens, b)   # the reference-style, unbatched call gives the same
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                one = pd_module.pydisort(*args, **kwargs)
+            u1, d1 = sub.generate_diff_act_flux_funcs(one[3])
+            compare((u1(ens["tau_eval"][b]), d1(ens["tau_eval"][b])), (gold[f"{name}_up"][b], gold[f"{name}_down"][b]),
+                    (name, b, "unbatched"))
+    NQuad, leg, t1 = 8, gold["one_leg"], gold["one_tau"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = pd_module.pydisort(np.array([1.7]), np.array([0.9]), NQuad, leg[None, :], 0.6, 2.0, 0.3,
+                                 f_arr=gold["one_f"], NT_cor=False)
+    up, down = sub.generate_diff_act_flux_funcs(out[3])
+    compare((up(t1), down(t1)), (gold["one_up"], gold["one_down"]), ("one layer",))
+    compare((up(t1, True), down(t1, True)), (gold["one_up_anti"], gold["one_down_anti"]), ("one layer, antiderivative",))
+    val, tau_back = up(t1, False, True)
+    np.testing.assert_array_equal(np.squeeze(tau_back), 1.7)   # `return_tau_arr` hands back the layer grid
+    return worst
 
 
 def check_interpolate_vs_golden(pd_module, name, tol=1e-9):

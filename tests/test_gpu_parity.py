@@ -51,6 +51,12 @@ def test_interpolate_at_user_polar_angles_on_the_device(name):
     parity_suite.check_interpolate_vs_golden(pd, name)
 
 
+def test_actinic_fluxes_vs_reference_golden():
+    """Row a13 (subroutines.py:258-318, _assemble_intensity_and_fluxes.py:360-371): actinic fluxes from k_eval_u0
+    with the delta-scaling reclassification, against the unmodified reference's (tests/golden/actinic.npz)."""
+    parity_suite.check_actinic_vs_golden(pd)
+
+
 def test_thermal_source_inputs_on_the_device():
     """Row f2 (subroutines.py:322-454): pd_planck_band / pd_s_poly_coeffs against the reference's helpers; the
     coefficients stay on the device and feed pydisort() directly."""
@@ -95,16 +101,21 @@ def test_hapke_fourier_modes_on_the_device_and_per_column_beam_directions():
             np.testing.assert_allclose(Fp[b], two[1](tau[b]), rtol=1e-6)
 
 
-@pytest.mark.parametrize("name,ncol,first", [("sw", 48, 1000), ("lw", 256, 5000), ("tp1", 6, 0), ("tp9c", 2, 0)])
-def test_ensembles_vs_live_oracle(name, ncol, first):
-    from oracle import disort_oracle
-    ens = synthetic.make(name, ncol, first)
-    got = parity_suite.run_batched(pd.pydisort, ens)
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        ref = synthetic.run_reference_like(disort_oracle.pydisort, ens)
-    tol = golden_io.conditioning_tolerance(ens["args"][1])
-    parity_suite.compare_fields(got, ref, ncol, tol, name)
+@pytest.fixture(scope="module")
+def oracle_pool():
+    """Host cores for the live oracle (BLAS threads pinned to one per process by conftest)."""
+    import multiprocessing as mp
+    import os
+    with mp.get_context("spawn").Pool(min(os.cpu_count() or 1, 32)) as pool:
+        yield pool
+
+
+@pytest.mark.parametrize("name,ncol,first", [("sw", 256, 1000), ("lw", 1024, 5000), ("ha", 64, 700), ("tp1", 6, 0),
+                                             ("tp9c", 2, 0)])
+def test_ensembles_vs_live_oracle(name, ncol, first, oracle_pool):
+    """SURVEY.md 8(d) sample sizes (256 SW / 1,024 LW / 64 HA columns): the CUDA path against the pinned oracle run
+    live on the host cores, both 8(c) criteria per column and field (parity_suite.compare_fields)."""
+    parity_suite.check_ensemble_vs_live_oracle(pd.pydisort, name, ncol, first, pool=oracle_pool)
 
 
 def test_batched_equals_column_by_column():

@@ -40,6 +40,16 @@ def test_interpolate_at_user_polar_angles(name):
     parity_suite.check_interpolate_vs_golden(pd, name)
 
 
+@pytest.mark.parametrize("name,ncol,first", [("sw", 4, 1000), ("lw", 16, 5000), ("ha", 1, 700), ("tp1", 6, 0), ("tp9c", 2, 0)])
+def test_ensemble_slices_vs_live_oracle(name, ncol, first):
+    """Small version of the GPU suite's 256 / 1,024 / 64-column comparison (same code path, no process pool)."""
+    parity_suite.check_ensemble_vs_live_oracle(pd.pydisort, name, ncol, first)
+
+
+def test_actinic_fluxes():
+    parity_suite.check_actinic_vs_golden(pd)
+
+
 def test_thermal_source_inputs():
     parity_suite.check_thermal_inputs_vs_golden(pd)
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Print the metrics we track for every kernel in an .ncu-rep (ncu --set full): python tools/ncu_summary.py rep [regex]"""
+"""Print the metrics we track for every kernel in an .ncu-rep (ncu --set full): python tools/ncu_summary.py rep.ncu-rep|raw.csv [regex]"""
 import csv, io, re, subprocess, sys
 WANT = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
         'launch__shared_mem_per_block_dynamic', 'sm__warps_active.avg.pct_of_peak_sustained_active',
@@ -22,7 +22,8 @@ WANT = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio']
 rep = sys.argv[1]
 pat = re.compile(sys.argv[2]) if len(sys.argv) > 2 else None
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+out = open(rep).read() if rep.endswith(".csv") else \
+    subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr, units = rows[0], rows[1]
 for r in rows[2:]:
