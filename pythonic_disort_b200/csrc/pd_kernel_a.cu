@@ -1,6 +1,7 @@
 // pd_kernel_a.cu -- stage A kernel: one lane group per (column, layer) item, one Fourier mode per blockIdx.y
 #include "pd_launch.h"
 #include "pd_stage_a_sym.cuh"
+#include "pd_stage_a_sym16.cuh"
 
 template <int LANES, int NC>
 __global__ void k_stage_a(PdStageA a, const double* __restrict__ ptab, int items_per_cta, int item_doubles, int reps) {
@@ -75,6 +76,49 @@ __global__ void __launch_bounds__(PD_SYM_THREADS, ((N <= 4) ? 4 : 2) * (128 / PD
     if (!done) a.K[(((long)b * a.NF + m) * a.L + l) * N] = __longlong_as_double(0x7ff8000000000000LL);
 }
 
+// eight lanes per item, symmetric (Cholesky + two-sided Jacobi) path, N = 16
+#ifndef PD_J16_THREADS
+#define PD_J16_THREADS 64
+#endif
+#ifndef PD_J16_MINB
+#define PD_J16_MINB 5
+#endif
+__global__ void __launch_bounds__(PD_J16_THREADS, PD_J16_MINB) k_stage_a_j16(PdStageA a, const double* __restrict__ ptab) {
+    extern __shared__ double smem[];
+    const int m = blockIdx.y, nm = a.NLeg - m;
+    double* Qs = smem;            // [nm][16]
+    double* tab = Qs + 32 * 16;   // 0.5 / sqrt(w mu), 1 / mu
+    double* scratch = tab + 32;
+    for (int idx = threadIdx.x; idx < nm * 16; idx += blockDim.x) {
+        const int i = idx & 15;
+        Qs[idx] = ptab[((long)m * a.NLeg + m) * 16 + idx] * sqrt(a.w[i] / a.mu[i]);
+    }
+    if (threadIdx.x < 16) {
+        tab[threadIdx.x] = 0.5 * pd_rsqrt(a.w[threadIdx.x] * a.mu[threadIdx.x]);
+        tab[16 + threadIdx.x] = 1.0 / a.mu[threadIdx.x];
+    }
+    __syncthreads();
+    const long items = (long)a.B * a.L;
+    long it = (long)blockIdx.x * (PD_J16_THREADS / 8) + (threadIdx.x >> 3);
+    const bool valid = it < items;
+    if (!valid) it = items - 1;  // padding lanes of the last CTA run along (the warp's shuffles need them) without storing
+    const int b = (int)(it / a.L), l = (int)(it % a.L);
+    const bool done = pd_stage_a_j16_item(a, b, m, l, valid, Qs, tab, scratch + (long)(threadIdx.x >> 3) * PdJ16::ITEM);
+    if (valid && !done && (threadIdx.x & 7) == 0)
+        a.K[(((long)b * a.NF + m) * a.L + l) * 16] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
+static int launch_j16(const PdStageA& a, const double* ptab, cudaStream_t st) {
+    const int ipc = PD_J16_THREADS / 8;
+    const size_t smem = (size_t)(32 * 16 + 32 + ipc * PdJ16::ITEM) * 8;
+    cudaError_t e = cudaFuncSetAttribute(k_stage_a_j16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const long items = (long)a.B * a.L;
+    dim3 grid((unsigned)((items + ipc - 1) / ipc), a.NF);
+    k_stage_a_j16<<<grid, PD_J16_THREADS, smem, st>>>(a, ptab);
+    return (int)cudaGetLastError();
+}
+
 template <int N>
 static int launch_sym(const PdStageA& a, const double* ptab, cudaStream_t st) {
     using P = PdSym<N>;
@@ -90,8 +134,8 @@ static int launch_sym(const PdStageA& a, const double* ptab, cudaStream_t st) {
 int pd_launch_stage_a(const PdStageA& a_in, int flags, const double* ptab, cudaStream_t st) {
     PdStageA a = a_in;
     a.only_flagged = 0;
-    if ((a.N == 4 || a.N == 8) && !(flags & PD_FLAG_GENERIC_KERNELS)) {  // symmetric fast path first; the general kernel then only redoes flagged items
-        const int rc = (a.N == 4) ? launch_sym<4>(a, ptab, st) : launch_sym<8>(a, ptab, st);
+    if ((a.N == 4 || a.N == 8 || (a.N == 16 && a.NLeg <= 32)) && !(flags & PD_FLAG_GENERIC_KERNELS)) {  // symmetric fast path first; the general kernel then only redoes flagged items
+        const int rc = (a.N == 4) ? launch_sym<4>(a, ptab, st) : (a.N == 8) ? launch_sym<8>(a, ptab, st) : launch_j16(a, ptab, st);
         if (rc) return rc;
         a.only_flagged = 1;
     }
