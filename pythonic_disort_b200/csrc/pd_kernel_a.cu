@@ -81,9 +81,14 @@ __global__ void __launch_bounds__(PD_SYM_THREADS, ((N <= 4) ? 4 : 2) * (128 / PD
 #define PD_J16_THREADS 64
 #endif
 #ifndef PD_J16_MINB
-#define PD_J16_MINB 5
+#define PD_J16_MINB 4
 #endif
-__global__ void __launch_bounds__(PD_J16_THREADS, PD_J16_MINB) k_stage_a_j16(PdStageA a, const double* __restrict__ ptab) {
+#ifdef PD_J16_MAXREG
+__global__ void __maxnreg__(PD_J16_MAXREG) k_stage_a_j16(
+#else
+__global__ void __launch_bounds__(PD_J16_THREADS, PD_J16_MINB) k_stage_a_j16(
+#endif
+    PdStageA a, const double* __restrict__ ptab) {
     extern __shared__ double smem[];
     const int m = blockIdx.y, nm = a.NLeg - m;
     double* Qs = smem;            // [nm][16]

@@ -8,9 +8,9 @@
 // A 16 x 16 matrix does not fit one thread's registers, so the item is spread over 8 lanes, lane `lam` holding two
 // COLUMNS of every matrix.  T is diagonalised by two-sided Jacobi rotations in the odd-even transposition ordering
 // (16 steps per sweep: even steps rotate the column pairs (2i, 2i+1), odd steps the pairs (2i+1, 2i+2), and the two
-// columns of a pair swap places after their rotation, so every pair meets once per sweep).  In an even step the pair
-// of a lane is its own two columns; for an odd step every lane passes its first column to the left neighbour (32
-// doubles with W, by shuffles), rotates what it now holds, and passes it back.  Row indices are kept RELATIVE to the
+// columns of a pair swap places after their rotation, so every pair meets once per sweep).  A lane always rotates the
+// two columns it holds; after every step it keeps its second column and takes the first column of its right neighbour
+// (32 doubles with W, by shuffles), which turns the even pairing into the odd one and back.  Row indices are kept RELATIVE to the
 // lane's first column, rho = (row - first column) mod 16: the pivot block is then always rows 0 and 1, the row pairs
 // are always (2j, 2j+1) with the rotation of lane lam + j, and every register index is a compile-time constant --
 // frame changes are renamings of registers.  Jacobi keeps the small eigenvalues of near-conservative layers to high
@@ -59,67 +59,65 @@ __device__ __forceinline__ void pd_j16_load_abs(const double* base, double (&v)[
 }
 
 // One Jacobi step on the pair a lane holds: A, B = the pair's columns of T (relative rows, pivot block at rows 0, 1),
-// Wa, Wb = the same columns of the accumulated rotations (absolute rows).  ODD: lane 7 holds the two end columns of
-// the line (15 and 0), which are not a pair: it rotates by the identity and does not swap.
-template <bool ODD>
+// Wa, Wb = the same columns of the accumulated rotations (absolute rows).  `idle`: in an odd step one lane holds the
+// two end columns of the line (15 and 0), which are not a pair; it "rotates" by a quarter turn (c = 0, s = 1), which
+// together with the swap leaves both columns where they are and flips the sign of one of them -- a similarity
+// transform like any other (an eigenvector changes sign), so no lane and no row pair needs a special case.
 __device__ __forceinline__ void pd_j16_step(double (&A)[16], double (&B)[16], double (&Wa)[16], double (&Wb)[16], int lam,
-                                            int grp, bool frozen) {
-    const bool idle = ODD && lam == 7;
+                                            int grp, bool frozen, bool idle) {
     const double app = A[0], aqq = B[1], apq = B[0];
     // t = tan(rotation angle) = sgn(d) 2 apq / (|d| + sqrt(d^2 + 4 apq^2)), d = aqq - app  (as in pd_stage_a_sym.cuh)
-    const bool tiny = frozen || idle || (apq * apq <= 1e-36 * fabs(app * aqq));
+    const bool tiny = frozen || (apq * apq <= 1e-36 * fabs(app * aqq));
     const double d = aqq - app, a2 = 2.0 * apq;
     const double h = fma(d, d, a2 * a2);
     const double den = fabs(d) + h * pd_rsqrt(h > 0.0 ? h : 1.0);
     const double tn = tiny ? 0.0 : ((d >= 0.0) ? a2 : -a2) * pd_rcp(den > 0.0 ? den : 1.0);
-    const double c = pd_rsqrt(fma(tn, tn, 1.0));
-    const double s = tn * c;
+    const double c0 = pd_rsqrt(fma(tn, tn, 1.0));
+    const double c = idle ? 0.0 : c0, s = idle ? 1.0 : tn * c0;
     // columns: new_p = c p - s q, new_q = s p + c q; the rotated columns swap places (new_q first)
 #pragma unroll
     for (int r = 2; r < 16; ++r) {
         const double p = A[r], q = B[r];
-        const double np = fma(c, p, -s * q), nq = fma(s, p, c * q);
-        A[r] = (ODD && idle) ? np : nq;
-        B[r] = (ODD && idle) ? nq : np;
+        A[r] = fma(s, p, c * q);
+        B[r] = fma(c, p, -s * q);
     }
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
         const double p = Wa[r], q = Wb[r];
-        const double np = fma(c, p, -s * q), nq = fma(s, p, c * q);
-        Wa[r] = (ODD && idle) ? np : nq;
-        Wb[r] = (ODD && idle) ? nq : np;
+        Wa[r] = fma(s, p, c * q);
+        Wb[r] = fma(c, p, -s * q);
     }
-    if (!(ODD && idle)) {  // pivot block, exact: the first slot now holds column q
-        const double tpq = tiny ? apq : 0.0;
-        A[0] = fma(tn, apq, aqq);
+    {  // pivot block, exact: the first slot now holds column q
+        const double tpq = idle ? -apq : (tiny ? apq : 0.0);
+        A[0] = idle ? app : fma(tn, apq, aqq);
         A[1] = tpq;
         B[0] = tpq;
-        B[1] = fma(-tn, apq, app);
+        B[1] = idle ? aqq : fma(-tn, apq, app);
     }
     // rows (2j, 2j+1) are the pair of lane lam + j: same rotation, same swap
 #pragma unroll
     for (int j = 1; j < 8; ++j) {
         const int src = grp | ((lam + j) & 7);
         const double cj = __shfl_sync(0xffffffffu, c, src), sj = __shfl_sync(0xffffffffu, s, src);
-        const bool noswap = ODD && ((lam + j) & 7) == 7;
         {
             const double p = A[2 * j], q = A[2 * j + 1];
-            const double np = fma(cj, p, -sj * q), nq = fma(sj, p, cj * q);
-            A[2 * j] = noswap ? np : nq;
-            A[2 * j + 1] = noswap ? nq : np;
+            A[2 * j] = fma(sj, p, cj * q);
+            A[2 * j + 1] = fma(cj, p, -sj * q);
         }
         {
             const double p = B[2 * j], q = B[2 * j + 1];
-            const double np = fma(cj, p, -sj * q), nq = fma(sj, p, cj * q);
-            B[2 * j] = noswap ? np : nq;
-            B[2 * j + 1] = noswap ? nq : np;
+            B[2 * j] = fma(sj, p, cj * q);
+            B[2 * j + 1] = fma(cj, p, -sj * q);
         }
     }
 }
 
-// even frame (lane holds columns 2 lam, 2 lam + 1) -> odd frame (2 lam + 1, 2 lam + 2; lane 7: 15 and 0)
-__device__ __forceinline__ void pd_j16_to_odd(double (&A)[16], double (&B)[16], double (&Wa)[16], double (&Wb)[16], int lam,
-                                              int grp) {
+// After every step the frame moves on by one column: the lane keeps its second column as the new first one and takes
+// the first column of its right neighbour (lane 7 from lane 0: the line of columns is handled as a ring, the pair
+// that closes it is the idle one).  After n shifts lane lam holds columns 2 lam + n and 2 lam + n + 1 (mod 16); 16
+// shifts -- one sweep -- bring every column home.
+__device__ __forceinline__ void pd_j16_shift(double (&A)[16], double (&B)[16], double (&Wa)[16], double (&Wb)[16], int lam,
+                                             int grp) {
     const int src = grp | ((lam + 1) & 7);
     double nA[16], nB[16];
 #pragma unroll
@@ -134,24 +132,6 @@ __device__ __forceinline__ void pd_j16_to_odd(double (&A)[16], double (&B)[16], 
         const double t = __shfl_sync(0xffffffffu, Wa[r], src);
         Wa[r] = Wb[r];
         Wb[r] = t;
-    }
-}
-__device__ __forceinline__ void pd_j16_to_even(double (&A)[16], double (&B)[16], double (&Wa)[16], double (&Wb)[16], int lam,
-                                               int grp) {
-    const int src = grp | ((lam + 7) & 7);
-    double nA[16], nB[16];
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        nA[r] = __shfl_sync(0xffffffffu, B[(r + 1) & 15], src);
-        nB[r] = A[(r + 15) & 15];
-    }
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        A[r] = nA[r];
-        B[r] = nB[r];
-        const double t = __shfl_sync(0xffffffffu, Wb[r], src);
-        Wb[r] = Wa[r];
-        Wa[r] = t;
     }
 }
 
@@ -184,8 +164,28 @@ __device__ __forceinline__ bool pd_stage_a_j16_item(const PdStageA& a, int b, in
     double* V0 = sm + P::OFF_V0;
     double* V1 = sm + P::OFF_V1;
 
+    // omega* (2l+1) g*_l and the beam coefficients of this item, fetched by the 8 lanes together (L's buffer is free
+    // until the factorisation starts)
+    double* CW = LL;
+    double* CB = LL + 32;
+    const double mu0 = a.colp[(long)b * PD_NCOLP + PD_COL_MU0];
+    const double fac = beam ? a.colp[(long)b * PD_NCOLP + PD_COL_I0] / (4.0 * PD_PI) * ((m == 0) ? 1.0 : 2.0) : 0.0;
     bool active = false;  // _solve_for_gen_and_part_sols.py:119
-    for (int t = 0; t < nm; ++t) active |= (fabs((omega / 2) * wl[t]) > 1e-8);
+    {
+        const double* pm0 = a.pmu0 + ((long)b * a.NF + m) * a.NLeg + m;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int t = k * 8 + lam;
+            if (t < nm) {
+                const double w = wl[t];
+                active |= (fabs((omega / 2) * w) > 1e-8);
+                CW[t] = omega * w;
+                CB[t] = beam ? fac * (omega * w) * pm0[t] : 0.0;
+            }
+        }
+        active = (__ballot_sync(0xffffffffu, active) & (0xffu << grp)) != 0u;  // also orders the stores above
+        __syncwarp();
+    }
 
     // ---- X' and S, two columns each (relative rows), beam source vectors for the lane's two streams ----
     double x1a = 0.0, x1b = 0.0, x2a = 0.0, x2b = 0.0, ra = 0.0, rb = 0.0, da = 0.0, db = 0.0;
@@ -201,11 +201,8 @@ __device__ __forceinline__ bool pd_stage_a_j16_item(const PdStageA& a, int b, in
             XA[0] = SA[0] = m0;
             XB[1] = SB[1] = m1;
         }
-        const double mu0 = a.colp[(long)b * PD_NCOLP + PD_COL_MU0];
-        const double fac = beam ? a.colp[(long)b * PD_NCOLP + PD_COL_I0] / (4.0 * PD_PI) * ((m == 0) ? 1.0 : 2.0) : 0.0;
-        const double* pm0 = a.pmu0 + ((long)b * a.NF + m) * a.NLeg + m;
         for (int t = 0; t < nm; ++t) {
-            const double c = omega * wl[t];
+            const double c = CW[t];
             double q[16];
             pd_j16_load_rel(Qs + t * 16, lam, q);
             const double ca = -c * q[0], cb = -c * q[1];
@@ -223,7 +220,7 @@ __device__ __forceinline__ bool pd_stage_a_j16_item(const PdStageA& a, int b, in
                 }
             }
             if (beam) {
-                const double cbm = fac * c * pm0[t];
+                const double cbm = CB[t];
                 const double va = cbm * q[0], vb = cbm * q[1];
                 x1a += va;
                 x1b += vb;
@@ -255,6 +252,7 @@ __device__ __forceinline__ bool pd_stage_a_j16_item(const PdStageA& a, int b, in
             pd_st2(V1 + 2 * lam, ra, rb);
         }
 
+        __syncwarp();  // the coefficient lists in L's buffer have been read
         // ---- Cholesky S = L L^T, right-looking: the owner of column j publishes it, everybody updates ----
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -357,11 +355,9 @@ __device__ __forceinline__ bool pd_stage_a_j16_item(const PdStageA& a, int b, in
         converged = (off <= 2e-17 * dg);
         if (__all_sync(0xffffffffu, converged)) break;
 #pragma unroll 1
-        for (int st = 0; st < 8; ++st) {
-            pd_j16_step<false>(TA, TB, Wa, Wb, lam, grp, converged);
-            pd_j16_to_odd(TA, TB, Wa, Wb, lam, grp);
-            pd_j16_step<true>(TA, TB, Wa, Wb, lam, grp, converged);
-            pd_j16_to_even(TA, TB, Wa, Wb, lam, grp);
+        for (int st = 0; st < 16; ++st) {  // even steps: pairs (2i, 2i+1); odd steps: (2i+1, 2i+2), one lane idle
+            pd_j16_step(TA, TB, Wa, Wb, lam, grp, converged, (st & 1) && lam == ((7 - (st >> 1)) & 7));
+            pd_j16_shift(TA, TB, Wa, Wb, lam, grp);
         }
     }
     const double lama = TA[0], lamb = TB[1];
