@@ -35,20 +35,33 @@ template <int N, int LS = 1>
 struct PdStageBAdd {
     static_assert(N >= 2 && N % 2 == 0, "N must be even");
     static constexpr int N2 = 2 * N, NN = N * N;
-    static constexpr int LAYER = 2 * NN + N + N2;          // one staged layer: G blocks [2][N][N], k [N], beam vector [2N]
+    // Every N x N matrix in shared memory is stored by lines of N doubles (a line = a column of V^, U^, R^, T^, Rup
+    // or a row of the staged G blocks).  A lane reads and writes ITS OWN line j with 128-bit accesses; at N = 8 the
+    // lines j and j + 2 start in the same bank, at N = 16 all lines do.  Position p of line l therefore lives at
+    // p ^ sw(l): the four / eight lanes of a quarter warp (what one 128-bit wavefront serves) then touch distinct
+    // banks, and a broadcast read of line l applies the same compile-time sw(l) (ncu on the unswizzled kernel: 36 %
+    // of the shared-memory wavefronts were bank conflicts, all of them on own-line accesses, the staging copies and
+    // the pivot-column publication).
+    PD_HD static constexpr int sw(int l) {
+        return (LS == 4 && N == 8) ? ((l & 2) << 1) : (LS == 8 && N == 8) ? (((l >> 1) & 3) << 1) : (LS > 1 && N == 16) ? ((l & 7) << 1) : 0;
+    }
+    static constexpr int LDM = N;
+    static constexpr int MAT = N * LDM;
+    static constexpr int LAYER = 2 * MAT + N + N2;         // one staged layer: G blocks [2][N][N], k [N], beam vector [2N]
     static constexpr int NVEC = 6;
     static constexpr int OFF_RING = 0;                     // [LAYER]: the layer in use; the next one is fetched into the
                                                            // same place as soon as this one has been unpacked
     static constexpr int OFF_VC = OFF_RING + LAYER;        // V^ column-major; later the columns of R^ (or of R^_s)
-    static constexpr int OFF_UC = OFF_VC + NN;             // U^ column-major; later the columns of T^
-    static constexpr int OFF_WC = OFF_UC + NN;             // columns of Rup
-    static constexpr int OFF_CB = OFF_WC + NN;             // [2][2N] pivot columns (double buffered)
+    static constexpr int OFF_UC = OFF_VC + MAT;            // U^ column-major; later the columns of T^
+    static constexpr int OFF_WC = OFF_UC + MAT;            // columns of Rup
+    static constexpr int OFF_CB = OFF_WC + MAT;            // [2][2N] pivot columns (double buffered)
     static constexpr int OFF_VEC = OFF_CB + 4 * N;         // [NVEC][N] vectors every lane needs
     static constexpr int RAW = OFF_VEC + NVEC * N;
-    // stride between the systems of a warp = LS (mod 16) doubles: a 128-bit broadcast read serves a quarter warp
-    // (8 / LS systems), a 64-bit per-lane access a half warp (16 / LS systems of LS consecutive doubles each); both
-    // then touch every bank once
-    static constexpr int SD = ((RAW + 15) & ~15) + ((LS < 2 ? 2 : LS) % 16);
+    // stride between the systems of a warp.  N = 8 (four lanes per system, two systems per quarter warp): 2 (mod 16)
+    // doubles = 16 bytes, so that the swizzled own-line accesses of the two systems interleave and the eight single
+    // lanes that publish a pivot column hit eight different 16-byte slots.  Otherwise LS (mod 16) doubles: a 64-bit
+    // access of LS consecutive doubles per system then touches every bank once per half warp.
+    static constexpr int SD = ((RAW + 15) & ~15) + ((N == 8 && LS == 4) ? 2 : ((LS < 2 ? 2 : LS) % 16));
     static constexpr long HIST_PER_LAYER = 2 * NN + N2;    // Q^T, (Rup Q)^T, q, Rup q + S
 };
 
@@ -68,7 +81,11 @@ PD_HD double pd_add_gj_solve(const Grp& g, int lane, double (&Mc)[N / Grp::size]
         PD_FOR_OWN(jj, j)
             if (j == s) {
 #pragma unroll
-                for (int i = 0; i < N; ++i) cb[i] = Mc[jj][i];
+                for (int i = 0; i < N; i += 2) {
+                    pd_d2 c2;
+                    c2.x = Mc[jj][i]; c2.y = Mc[jj][i + 1];
+                    *reinterpret_cast<pd_d2*>(cb + i) = c2;
+                }
                 cb[N] = vq[jj];
             }
         g.sync();
@@ -101,7 +118,7 @@ PD_HD double pd_add_gj_solve(const Grp& g, int lane, double (&Mc)[N / Grp::size]
 template <class Grp, int N>
 PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double* sm, double* hist) {
     using F = PdStageBAdd<N, Grp::size>;
-    constexpr int LS = Grp::size, NJ = N / LS, N2 = 2 * N, NN = N * N;
+    constexpr int LS = Grp::size, NJ = N / LS, N2 = 2 * N, NN = N * N, LD = F::LDM, MAT = F::MAT;
     static_assert(N % LS == 0, "lanes per system must divide N");
     const int lane = g.lane();
     const int L = A.L;
@@ -136,15 +153,19 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
         const double* gs = Gc + (long)ll * 2 * NN;
         const double* ks = Kc + (long)ll * N;
 #if defined(__CUDA_ARCH__)
-        for (int ch = lane; ch < NN; ch += LS) pd_cp_async16(dst + 2 * ch, gs + 2 * ch);
-        for (int ch = lane; ch < N / 2; ch += LS) pd_cp_async16(dst + 2 * NN + 2 * ch, ks + 2 * ch);
+        for (int ch = lane; ch < NN; ch += LS) {  // 16-byte chunk ch = (row ch / (N/2), column pair ch % (N/2)) of [2N][N]
+            const int r = ch / (N / 2), c2 = 2 * (ch % (N / 2));
+            pd_cp_async16(dst + r * LD + (c2 ^ F::sw(r)), gs + 2 * ch);
+        }
+        for (int ch = lane; ch < N / 2; ch += LS) pd_cp_async16(dst + 2 * MAT + 2 * ch, ks + 2 * ch);
         if (Bc)
-            for (int ch = lane; ch < N; ch += LS) pd_cp_async16(dst + 2 * NN + N + 2 * ch, Bc + (long)ll * N2 + 2 * ch);
+            for (int ch = lane; ch < N; ch += LS) pd_cp_async16(dst + 2 * MAT + N + 2 * ch, Bc + (long)ll * N2 + 2 * ch);
 #else
-        for (int i = 0; i < 2 * NN; ++i) dst[i] = gs[i];
-        for (int i = 0; i < N; ++i) dst[2 * NN + i] = ks[i];
+        for (int i = 0; i < 2 * N; ++i)
+            for (int k = 0; k < N; ++k) dst[i * LD + (k ^ F::sw(i))] = gs[i * N + k];
+        for (int i = 0; i < N; ++i) dst[2 * MAT + i] = ks[i];
         if (Bc)
-            for (int i = 0; i < N2; ++i) dst[2 * NN + N + i] = Bc[(long)ll * N2 + i];
+            for (int i = 0; i < N2; ++i) dst[2 * MAT + N + i] = Bc[(long)ll * N2 + i];
 #endif
     };
     auto stage_wait = [&]() {
@@ -163,8 +184,8 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
             const double h = 0.5 * Dj[jj];
 #pragma unroll
             for (int k = 0; k < N; k += 2) {
-                const pd_d2 gp = *reinterpret_cast<const pd_d2*>(Gl + j * N + k);
-                const pd_d2 gm = *reinterpret_cast<const pd_d2*>(Gl + NN + j * N + k);
+                const pd_d2 gp = *reinterpret_cast<const pd_d2*>(Gl + j * LD + (k ^ F::sw(j)));
+                const pd_d2 gm = *reinterpret_cast<const pd_d2*>(Gl + MAT + j * LD + (k ^ F::sw(N + j)));
                 vrow[jj][k] = h * (gp.x + gm.x);
                 vrow[jj][k + 1] = h * (gp.y + gm.y);
                 urow[jj][k] = h * (gp.x - gm.x);
@@ -172,8 +193,8 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
             }
 #pragma unroll
             for (int k = 0; k < N; ++k) {
-                Vc[k * N + j] = vrow[jj][k];
-                Uc[k * N + j] = urow[jj][k];
+                Vc[k * LD + (j ^ F::sw(k))] = vrow[jj][k];
+                Uc[k * LD + (j ^ F::sw(k))] = urow[jj][k];
             }
         }
         g.sync();
@@ -196,7 +217,7 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
             const double c = coef[k];
 #pragma unroll
             for (int i = 0; i < N; i += 2) {
-                const pd_d2 mv = *reinterpret_cast<const pd_d2*>(Mcm + k * N + i);
+                const pd_d2 mv = *reinterpret_cast<const pd_d2*>(Mcm + k * LD + (i ^ F::sw(k)));
                 acc[i] = fma(mv.x, c, acc[i]);
                 acc[i + 1] = fma(mv.y, c, acc[i + 1]);
             }
@@ -235,7 +256,7 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             Rup[jj][i] = 0.0;
-            Wc[j * N + i] = 0.0;
+            Wc[j * LD + (i ^ F::sw(j))] = 0.0;
         }
         S[jj] = Dj[jj] * (have_b ? bneg[j] : 0.0);
     }
@@ -244,7 +265,7 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
     for (int l = 0; l < L; ++l) {
         stage_wait();
         const double* Gl = ring;
-        const double* Kl = Gl + 2 * NN;
+        const double* Kl = Gl + 2 * MAT;
         const double* Bl = Kl + N;
         const double dtau = taus[l + 1] - taus[l];
         const double att_b = beam ? exp(-taus[l + 1] * rmu0) : 0.0;
@@ -259,8 +280,8 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
                 double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                 for (int i = 0; i < N; i += 2) {
-                    const pd_d2 v2 = *reinterpret_cast<const pd_d2*>(Vc + k * N + i);
-                    const pd_d2 u2 = *reinterpret_cast<const pd_d2*>(Uc + k * N + i);
+                    const pd_d2 v2 = *reinterpret_cast<const pd_d2*>(Vc + k * LD + (i ^ F::sw(k)));
+                    const pd_d2 u2 = *reinterpret_cast<const pd_d2*>(Uc + k * LD + (i ^ F::sw(k)));
                     s0 = fma(v2.x, u2.x, s0);
                     s1 = fma(v2.y, u2.y, s1);
                 }
@@ -300,9 +321,11 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
                 PD_FOR_OWN(jj, j)
                     if (j == s) {
 #pragma unroll
-                        for (int i = 0; i < N; ++i) {
-                            cb[i] = X1[jj][i];
-                            cb[N + i] = X2[jj][i];
+                        for (int i = 0; i < N; i += 2) {
+                            pd_d2 a2, b2;
+                            a2.x = X1[jj][i]; a2.y = X1[jj][i + 1]; b2.x = X2[jj][i]; b2.y = X2[jj][i + 1];
+                            *reinterpret_cast<pd_d2*>(cb + i) = a2;
+                            *reinterpret_cast<pd_d2*>(cb + N + i) = b2;
                         }
                     }
                 g.sync();
@@ -336,8 +359,13 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
                 for (int i = 0; i < N; ++i) {
                     Rh[jj][i] = X1[jj][i] - X2[jj][i];
                     Th[jj][i] = X1[jj][i] + X2[jj][i] - ((i == j) ? 1.0 : 0.0);
-                    Rc[j * N + i] = Rh[jj][i];
-                    Tc[j * N + i] = Th[jj][i];
+                }
+#pragma unroll
+                for (int i = 0; i < N; i += 2) {
+                    pd_d2 r2, t2;
+                    r2.x = Rh[jj][i]; r2.y = Rh[jj][i + 1]; t2.x = Th[jj][i]; t2.y = Th[jj][i + 1];
+                    *reinterpret_cast<pd_d2*>(Rc + j * LD + (i ^ F::sw(j))) = r2;
+                    *reinterpret_cast<pd_d2*>(Tc + j * LD + (i ^ F::sw(j))) = t2;
                 }
             }
         }
@@ -398,7 +426,11 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
             add_cols(Rup[jj], Tc, RQ[jj]);
             S[jj] = sminus[jj] + dot_own(Th[jj], vec + 5 * N);
 #pragma unroll
-            for (int i = 0; i < N; ++i) Wc[j * N + i] = Rup[jj][i];
+            for (int i = 0; i < N; i += 2) {
+                pd_d2 w2;
+                w2.x = Rup[jj][i]; w2.y = Rup[jj][i + 1];
+                *reinterpret_cast<pd_d2*>(Wc + j * LD + (i ^ F::sw(j))) = w2;
+            }
         }
         att_t = att_b;
     }
@@ -423,7 +455,7 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
             const double fac = (m == 0) ? 2.0 : 1.0;
             for (int idx = lane; idx < NN; idx += LS) {
                 const int k = idx / N, i = idx - k * N;
-                Rc[idx] = fac * qm[i * N + k] * sqrt(A.w[i] * A.mu[i] * A.w[k] * A.mu[k]);
+                Rc[k * LD + (i ^ F::sw(k))] = fac * qm[i * N + k] * sqrt(A.w[i] * A.mu[i] * A.w[k] * A.mu[k]);
             }
 #pragma unroll
             PD_FOR_OWN(ii, i) vec[i] = S[ii];
@@ -441,7 +473,7 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
                 add_cols(Mc[jj], Rc, coef);  // column j of I - R^_s Rup
                 double s = bs[jj];           // row j of R^_s times S
 #pragma unroll
-                for (int k = 0; k < N; ++k) s = fma(Rc[k * N + j], vec[k], s);
+                for (int k = 0; k < N; ++k) s = fma(Rc[k * LD + (j ^ F::sw(k))], vec[k], s);
                 vq[jj] = s;
             }
             const double mp = pd_add_gj_solve<Grp, N, false>(g, lane, Mc, Y, vq, cbuf);
@@ -484,7 +516,7 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
         PD_FOR_OWN(ii, i) vec[i] = ubp[ii];
         stage_wait();
         const double* Gl = ring;
-        const double* Kl = Gl + 2 * NN;
+        const double* Kl = Gl + 2 * MAT;
         const double* Bl = Kl + N;
         double utp[NJ], utm[NJ];
 #pragma unroll
@@ -518,8 +550,8 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
             double g0 = 0.0, g1 = 0.0, s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
 #pragma unroll
             for (int i = 0; i < N; i += 2) {
-                const pd_d2 v2 = *reinterpret_cast<const pd_d2*>(Vc + k * N + i);
-                const pd_d2 u2 = *reinterpret_cast<const pd_d2*>(Uc + k * N + i);
+                const pd_d2 v2 = *reinterpret_cast<const pd_d2*>(Vc + k * LD + (i ^ F::sw(k)));
+                const pd_d2 u2 = *reinterpret_cast<const pd_d2*>(Uc + k * LD + (i ^ F::sw(k)));
                 const pd_d2 ps = *reinterpret_cast<const pd_d2*>(vec + N + i);
                 const pd_d2 ds = *reinterpret_cast<const pd_d2*>(vec + 2 * N + i);
                 g0 = fma(v2.x, u2.x, g0);
