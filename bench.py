@@ -163,7 +163,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # kernels launched per C-ABI call (label of the event mark api.py records around it)
 def _launches(label, N, nt):
-    return {"prologue": 1, "solve_eigen": 2 if N in (4, 8) else 1, "solve_bc": 2 if N in (2, 4, 8, 16) else 1,
+    return {"prologue": 1, "solve_eigen": 2 if N in (4, 8, 16) else 1, "solve_bc": 2 if N in (2, 4, 8, 16) else 1,
             "eval_flux": 1, "eval_u0": 1, "eval_u": 2 if nt else 1, "interp_mu": 1}.get(label, 1)
 
 
@@ -353,7 +353,7 @@ class Bench:
         item = NF * L
         bytes_k = {"solve_eigen": item * (NQuad + 1) * 8 + item * (2 * N * N + N + 2 * N) * 8,
                    "solve_bc": item * (2 * N * N + N + 2 * N) * 8 + item * 2 * N * 8}[dom]
-        kname = {"solve_eigen": "k_stage_a_sym" if N in (4, 8) else "k_stage_a",
+        kname = {"solve_eigen": "k_stage_a_sym" if N in (4, 8) else "k_stage_a_j16" if N == 16 else "k_stage_a",
                  "solve_bc": "k_stage_b_add" if N in (2, 4, 8, 16) else "k_stage_b"}[dom]
         per_col = self.traffic.get(workload, {}).get(kname)
         peak = self.fp64_peak

@@ -202,7 +202,10 @@ class _Solution:
         return out, nmu
 
     def eval_flux(self, tau, anti):
-        memo = getattr(self, "_flux_memo", None)  # flux_up(tau) then flux_down(tau): one launch serves both
+        # flux_up(tau) then flux_down(tau) on the same array object: one launch serves the pair.  The memo is consumed
+        # by its first hit, so it never outlives that pair (an array edited in place between later calls, or a caller
+        # writing into a returned tensor, cannot meet a stale entry); up / diffuse / direct are disjoint rows of `out`.
+        memo, self._flux_memo = getattr(self, "_flux_memo", None), None
         if memo is not None and memo[0] is tau and memo[1] == bool(anti) and memo[4] == _content_tag(tau):
             return memo[2], memo[3]
         tq, _ = self._tau_points(tau)

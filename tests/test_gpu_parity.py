@@ -118,6 +118,40 @@ def test_ensembles_vs_live_oracle(name, ncol, first, oracle_pool):
     parity_suite.check_ensemble_vs_live_oracle(pd.pydisort, name, ncol, first, pool=oracle_pool)
 
 
+def test_nquad32_with_thermal_source_and_sparse_phase_functions():
+    """NQuad = 32 outside the HA ensemble: the eight-lane symmetric eigen kernel (pd_stage_a_sym16.cuh) hands the
+    mode-0 items of a thermal problem to the general kernel, takes the shortcut for layers without scattering
+    (_solve_for_gen_and_part_sols.py:119, :162-168) and pads the last CTA when the item count is not a multiple of
+    its eight items; checked against the oracle."""
+    from oracle import disort_oracle
+    rng = np.random.default_rng(11)
+    B, L, NQuad = 3, 7, 32
+    tau = np.cumsum(rng.uniform(0.05, 0.8, (B, L)), axis=1)
+    omega = rng.uniform(0.1, 0.95, (B, L))
+    omega[:, 2] = 0.0          # a purely absorbing layer: every mode takes the shortcut
+    g = rng.uniform(0.2, 0.8, (B, L))
+    Leg = g[:, :, None] ** np.arange(NQuad + 1)[None, None, :]
+    Leg[0, 4, 6:] = 0.0        # a phase function with few moments: the high modes of that layer take the shortcut
+    planck = np.sort(rng.uniform(20, 90, (B, L + 1)), axis=1)
+    lev = np.concatenate([np.zeros((B, 1)), tau], axis=1)
+    slope = np.diff(planck, axis=1) / np.diff(lev, axis=1)
+    s_poly = np.stack([planck[:, :-1] - slope * lev[:, :-1], slope], axis=2)
+    mu0 = np.array([0.35, 0.62, 0.9])
+    kw = dict(s_poly_coeffs=s_poly, b_pos=0.9 * planck[:, -1:], BDRF_Fourier_modes=[0.1])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = pd.pydisort(tau, omega, NQuad, Leg, mu0, np.full(B, 2.0), 0.0, **kw)
+        Fp, (Fd, Fdir), u = out[1](lev), out[2](lev), out[4](lev, np.array([0.0, 2.0]))
+        for b in range(B):
+            ref = disort_oracle.pydisort(tau[b], omega[b], NQuad, Leg[b], mu0[b], 2.0, 0.0, s_poly_coeffs=s_poly[b],
+                                         b_pos=float(0.9 * planck[b, -1]), BDRF_Fourier_modes=[0.1])
+            scale = np.max(np.abs(ref[1](lev[b])))
+            assert np.max(np.abs(Fp[b] - ref[1](lev[b]))) <= 1e-9 * scale
+            assert np.max(np.abs(Fd[b] - ref[2](lev[b])[0])) <= 1e-9 * scale
+            ur = ref[4](lev[b], np.array([0.0, 2.0]))
+            assert np.max(np.abs(u[b] - ur)) <= 1e-9 * np.max(np.abs(ur))
+
+
 def test_batched_equals_column_by_column():
     ens = synthetic.make("sw", 5, 77)
     got = parity_suite.run_batched(pd.pydisort, ens)
