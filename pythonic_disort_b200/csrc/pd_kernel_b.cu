@@ -1,10 +1,13 @@
 // pd_kernel_b.cu -- stage B kernels: the boundary-condition solve of every (column, Fourier mode) system.
-//   k_stage_b_add<N>  production path (N = 2, 4, 8, 16): N lanes per system, block elimination over the interface
+//   k_stage_b_add<N>  production path (N = 8, 16): a lane group per system, block elimination over the interface
 //                     radiances (pd_stage_b_add.cuh); persistent grid, one history slot per resident system
+//   k_stage_b_tps<N>  production path (N = 2, 4): the same elimination with ONE THREAD per system, every matrix in
+//                     registers (pd_stage_b_tps.cuh); persistent grid, history interleaved over the threads
 //   k_stage_b<NC>     size-generic pivoted band solver (pd_stage_b.cuh), one warp per system: any N, the
 //                     PD_FLAG_GENERIC_KERNELS test path, and the second pass over systems the first kernel flagged
 #include "pd_launch.h"
 #include "pd_stage_b_add.cuh"
+#include "pd_stage_b_tps.cuh"
 
 template <int NC>
 __global__ void k_stage_b(PdStageB a, double* hist, long hist_doubles, int sys_doubles, const int32_t* only_flagged) {
@@ -22,20 +25,21 @@ __global__ void k_stage_b(PdStageB a, double* hist, long hist_doubles, int sys_d
     }
 }
 
-// Lanes per system: every N x N product needs N^2 operands per lane from other lanes (shared memory), however the
-// columns are dealt out; with two columns per lane each operand feeds two FMAs, which is what the shared-memory
-// pipe (one 128-byte wavefront per cycle per SM against two warp-wide DFMAs) needs to stay off the critical path.
-// N = 16 keeps one column per lane (two would spill); for N = 4 the per-lane transcendental and control overhead,
-// which doubles with two columns per lane, outweighs the products (measured: 56 against 43 ms per 1M LW columns).
+// Lanes per system (N = 8, 16): every N x N product needs N^2 operands per lane from other lanes (shared memory),
+// however the columns are dealt out; with two columns per lane each operand feeds two FMAs, which is what the
+// shared-memory pipe (one 128-byte wavefront per cycle per SM against two warp-wide DFMAs) needs to stay off the
+// critical path.  N = 16 keeps one column per lane (two would spill).  Measured on the SW ensemble (N = 8): four
+// lanes at 255 registers / 8 warps per SM and eight lanes at 128 registers / 16 warps per SM run within 3 % of each
+// other -- half the occupancy is paid for by half the operand traffic per FMA.
 #ifndef PD_ADD_LS
-#define PD_ADD_LS(N) ((N) == 8 ? 4 : (N))
+#define PD_ADD_LS(N) ((N) == 8 ? 4 : (N))  /* N = 8, 16 only: smaller systems take the one-thread-per-system kernel */
 #endif
 template <int N>
 struct AddCfg {
     static constexpr int LS = PD_ADD_LS(N);              // lanes per system
     static constexpr int THREADS = 64;                   // two warps per CTA
     static constexpr int SPC = THREADS / LS;             // systems per CTA
-    static constexpr int MINB = (N <= 4) ? 8 : 4;  // resident CTAs per SM the kernel is compiled for
+    static constexpr int MINB = 4;                       // resident CTAs per SM the kernel is compiled for
     using F = PdStageBAdd<N, LS>;
     static constexpr size_t SMEM = (size_t)F::SD * 8 * SPC;
 };
@@ -55,6 +59,44 @@ __global__ void __launch_bounds__(AddCfg<N>::THREADS, AddCfg<N>::MINB) k_stage_b
         const bool ok = pd_stage_b_add<SubWarp<Cf::LS>, N>(g, a, (int)(s / a.NF), (int)(s % a.NF), sm, h);
         if (!ok && g.lane() == 0) sysflag[s] = 1;  // redone by k_stage_b
     }
+}
+
+#ifndef PD_TPS_THREADS
+#define PD_TPS_THREADS 64
+#endif
+#ifndef PD_TPS_MINB
+#define PD_TPS_MINB 4
+#endif
+template <int N>
+__global__ void __launch_bounds__(PD_TPS_THREADS, PD_TPS_MINB) k_stage_b_tps(PdStageB a, double* hist, int32_t* sysflag) {
+    const long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long nslots = (long)gridDim.x * blockDim.x;
+    const long nsys = (long)a.B * a.NF;
+    for (long s = slot; s < nsys; s += nslots) {
+        const bool ok = pd_stage_b_tps<N>(a, (int)(s / a.NF), (int)(s % a.NF), hist + slot, nslots);
+        if (!ok) sysflag[s] = 1;  // redone by k_stage_b
+    }
+}
+
+template <int N>
+static void plan_tps(StageBPlan& p, long nsys, int L) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stage_b_tps<N>, PD_TPS_THREADS, 0) != cudaSuccess || occ < 1) {
+        cudaGetLastError();  // no device (sizing from a host-only process): plan for the compiled residency
+        occ = PD_TPS_MINB;
+    }
+    long blocks = (nsys + PD_TPS_THREADS - 1) / PD_TPS_THREADS;
+    if (blocks > (long)PD_NUM_SMS * occ) blocks = (long)PD_NUM_SMS * occ;
+    p.add = 2;
+    p.add_blocks = (int)blocks;
+    p.add_slots = blocks * PD_TPS_THREADS;
+    p.add_hist = (long)L * PdStageBTps<N>::HIST_PER_LAYER;
+}
+
+template <int N>
+static int launch_tps(const PdStageB& a, const StageBPlan& p, double* hist, int32_t* sysflag, cudaStream_t st) {
+    k_stage_b_tps<N><<<p.add_blocks, PD_TPS_THREADS, 0, st>>>(a, hist, sysflag);
+    return (int)cudaGetLastError();
 }
 
 template <int N>
@@ -90,8 +132,8 @@ StageBPlan pd_plan_stage_b(int B, int NF, int N, int L, int flags) {
     const long nsys = (long)B * NF;
     if (add_supported(N) && !(flags & PD_FLAG_GENERIC_KERNELS)) {
         switch (N) {
-            case 2: plan_add<2>(p, nsys, L); break;
-            case 4: plan_add<4>(p, nsys, L); break;
+            case 2: plan_tps<2>(p, nsys, L); break;
+            case 4: plan_tps<4>(p, nsys, L); break;
             case 8: plan_add<8>(p, nsys, L); break;
             default: plan_add<16>(p, nsys, L); break;
         }
@@ -137,8 +179,8 @@ int pd_launch_stage_b(const PdStageB& a, int flags, void* workspace, size_t work
         if (e != cudaSuccess) return (int)e;
         int rc;
         switch (a.N) {
-            case 2: rc = launch_add<2>(a, pb, hist, sysflag, st); break;
-            case 4: rc = launch_add<4>(a, pb, hist, sysflag, st); break;
+            case 2: rc = launch_tps<2>(a, pb, hist, sysflag, st); break;
+            case 4: rc = launch_tps<4>(a, pb, hist, sysflag, st); break;
             case 8: rc = launch_add<8>(a, pb, hist, sysflag, st); break;
             default: rc = launch_add<16>(a, pb, hist, sysflag, st); break;
         }

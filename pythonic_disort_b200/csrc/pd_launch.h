@@ -20,9 +20,9 @@ static inline cudaStream_t pd_stream(void* s) { return reinterpret_cast<cudaStre
 
 // Stage B launch plan and workspace layout: [system flags int32 | history of k_stage_b_add | history of k_stage_b]
 struct StageBPlan {
-    int add;                 // 1: k_stage_b_add runs first, k_stage_b only redoes the systems it flags
+    int add;                 // 1: k_stage_b_add (2: k_stage_b_tps) runs first, k_stage_b only redoes the systems it flags
     int add_blocks;
-    long add_slots, add_hist;  // resident systems and history doubles per system of k_stage_b_add
+    long add_slots, add_hist;  // resident systems and history doubles per system of that first kernel
     size_t flag_bytes;
     int wpb, sys_doubles, blocks;  // k_stage_b: warps per CTA, shared doubles per system, grid
     size_t smem;

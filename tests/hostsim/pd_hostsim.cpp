@@ -16,6 +16,7 @@
 #include "../../pythonic_disort_b200/csrc/pd_stage_a_sym.cuh"
 #include "../../pythonic_disort_b200/csrc/pd_stage_b.cuh"
 #include "../../pythonic_disort_b200/csrc/pd_stage_b_add.cuh"
+#include "../../pythonic_disort_b200/csrc/pd_stage_b_tps.cuh"
 
 template <int N>
 static bool host_stage_b_add(const PdStageB& sb, int b, int m, double* hist) {
@@ -114,15 +115,15 @@ int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const 
     sb.bdrf_q = bdrf_q; sb.bdrf_q0 = bdrf_q0; sb.K = K; sb.G = G; sb.Bv = Bv; sb.dth = dth; sb.C = C;
     sb.status = status;
     double* smb = (double*)malloc(sizeof(double) * (pd_stage_b_doubles(N) + 16));
-    // same dispatch as pd_launch_stage_b: interface-radiance elimination for N = 2, 4, 8, 16 (unless
+    // same dispatch as pd_launch_stage_b: interface-radiance elimination for N = 2, 4 (thread per system), 8, 16 (unless
     // PD_FLAG_GENERIC_KERNELS), pivoted band solver otherwise and for the systems the first one hands back
     const bool generic_b = (cfg->flags & PD_FLAG_GENERIC_KERNELS) != 0;
     for (int b = 0; b < cfg->B; ++b)
         for (int m = 0; m < cfg->NFourier; ++m) {
             bool ok = false;
             if (!generic_b) {
-                if (N == 2) ok = host_stage_b_add<2>(sb, b, m, (double*)workspace);
-                if (N == 4) ok = host_stage_b_add<4>(sb, b, m, (double*)workspace);
+                if (N == 2) ok = pd_stage_b_tps<2>(sb, b, m, (double*)workspace, 1);  // one thread per system
+                if (N == 4) ok = pd_stage_b_tps<4>(sb, b, m, (double*)workspace, 1);
                 if (N == 8) ok = host_stage_b_add<8>(sb, b, m, (double*)workspace);
                 if (N == 16) ok = host_stage_b_add<16>(sb, b, m, (double*)workspace);
             }
