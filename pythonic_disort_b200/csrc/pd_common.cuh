@@ -26,6 +26,7 @@ struct SerialGroup {
     PD_HD int lane() const { return 0; }
     PD_HD void sync() const {}
     PD_HD bool any(bool v) const { return v; }
+    PD_HD double shfl(double v, int) const { return v; }
 };
 
 #if defined(__CUDACC__)
@@ -43,6 +44,8 @@ struct SubWarp {
     __device__ __forceinline__ int lane() const { return ln; }
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
     __device__ __forceinline__ bool any(bool v) const { return (__ballot_sync(mask, v) & mask) != 0u; }
+    // value of `v` held by lane `src` of this group
+    __device__ __forceinline__ double shfl(double v, int src) const { return __shfl_sync(mask, v, src, LANES); }
 };
 
 // 16 bytes global -> shared without passing through registers (L2 only: the source may have been written by this kernel)

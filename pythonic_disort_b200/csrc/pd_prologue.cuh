@@ -52,8 +52,13 @@ PD_HD int pd_prologue_column(const Grp& g, const PdPrologue& a, int b) {
     int chk = 0;
 
     // ---- checks that need every element (each lane looks at a strided share) ----
-    bool fany = false;
-    for (int l = 0; l < L; ++l) fany = fany || (f && f[l] > 0.0);  // uniform across lanes
+    bool fany = false, wany = false;
+    for (int l = lane; l < L; l += Grp::size) {
+        fany = fany || (f && f[l] > 0.0);
+        wany = wany || (om[l] > 0.0);
+    }
+    fany = g.any(fany);  // uniform across lanes
+    wany = g.any(wany);
     for (int l = lane; l < L; l += Grp::size) {
         const double t = tau[l], th = t - (l ? tau[l - 1] : 0.0);
         if (!(t > 0.0)) chk |= PD_CHK_TAU_POS;
@@ -90,18 +95,28 @@ PD_HD int pd_prologue_column(const Grp& g, const PdPrologue& a, int b) {
             wleg[(long)l * a.NLeg + k] = gs * (2 * k + 1);
         }
     }
-    g.sync();
-    if (lane == 0) {  // cumulative scaled optical depth, summed top-down like np.cumsum
+    // cumulative scaled optical depth, summed top-down like np.cumsum: every lane brings one term of a chunk, the
+    // terms go round by shuffles and every lane adds them up in the same order (no serial chain of memory round trips)
+    if (lane == 0) taus[0] = 0.0;
+    if (fany) {
         double acc = 0.0;
-        taus[0] = 0.0;
-        for (int l = 0; l < L; ++l) {
-            if (fany) {
-                acc += scl[l] * (tau[l] - (l ? tau[l - 1] : 0.0));
-                taus[l + 1] = acc;
-            } else {
-                taus[l + 1] = tau[l];
+        for (int base = 0; base < L; base += Grp::size) {
+            const int l = base + lane;
+            double term = 0.0;
+            if (l < L) {
+                const double fl = f[l];
+                term = (1.0 - om[l] * fl) * (tau[l] - (l ? tau[l - 1] : 0.0));  // scl[l] as computed above
             }
+            double mine = 0.0;
+            const int cnt = (L - base < Grp::size) ? L - base : Grp::size;
+            for (int i = 0; i < cnt; ++i) {
+                acc += g.shfl(term, i);
+                if (lane == i) mine = acc;
+            }
+            if (l < L) taus[l + 1] = mine;
         }
+    } else {
+        for (int l = lane; l < L; l += Grp::size) taus[l + 1] = tau[l];
     }
     g.sync();
     // ---- thermal source polynomials: Kirchhoff weighting and, under delta-M, the
@@ -161,8 +176,6 @@ PD_HD int pd_prologue_column(const Grp& g, const PdPrologue& a, int b) {
         cp[PD_COL_PHI0] = phi0;
         cp[PD_COL_I0_RAW] = I0;
         cp[PD_COL_DM] = fany ? 1.0 : 0.0;
-        bool wany = false;
-        for (int l = 0; l < L; ++l) wany = wany || (om[l] > 0.0);
         cp[PD_COL_NT] = (I0 > 0.0 && fany && wany) ? 1.0 : 0.0;
         cp[7] = 0.0;
     }

@@ -1,6 +1,6 @@
 #!/bin/bash
-for v in base m6; do
-  if [ $v = base ]; then unset PD_LIB_PATH; else export PD_LIB_PATH=$PWD/gpurun_in_$v.so; fi
-  python bench.py --workload lw --columns 262144 --chunk 131072 --steps 3 --warmup 1 --no-cpu --no-others 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$v', round(d['value']), d['roofline']['kernel_ms_per_step_all'])"
+timeout 2400 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+for w in lw sw; do
+python bench.py --workload $w --steps 3 --warmup 2 --no-cpu --no-others 2>gpurun_out/r2g_err_$w.log | tee gpurun_out/r2g_bench_$w.json | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$w', round(d['value']), round(d['e2e']['value']), d['ms_per_step'], d['roofline']['kernel_ms_per_step_all'])"
 done
