@@ -75,8 +75,10 @@ typedef struct pd_config {
 
 int pd_abi_version(void);
 
-/* Scratch needed by pd_solve for this configuration (bytes, device memory).
- * The boundary-condition kernel keeps one LU panel history per resident warp. */
+/* Scratch needed by pd_solve / pd_solve_stages for this configuration (bytes, device memory, 256-byte aligned).
+ * Layout (private): a 256-byte head (counter of eigen items the symmetric kernels hand to the general one, so
+ * that the fallback pass can return at once), per-system flags, and the history of the boundary-condition sweep
+ * of every resident system (Q, Rup Q, q, Rup q + S per layer).  The library never allocates. */
 size_t pd_workspace_bytes(const pd_config* cfg);
 
 /* pydisort prologue: input checks, delta-M scaling, thermal-source rescaling

@@ -41,7 +41,7 @@ int pd_abi_version(void) { return PD_ABI_VERSION; }
 
 size_t pd_workspace_bytes(const pd_config* cfg) {
     if (pd_check_cfg(cfg)) return 0;
-    return pd_plan_stage_b(cfg->B, cfg->NFourier, cfg->NQuad / 2, cfg->L, cfg->flags).bytes();
+    return PD_WS_HEAD + pd_plan_stage_b(cfg->B, cfg->NFourier, cfg->NQuad / 2, cfg->L, cfg->flags).bytes();
 }
 
 int pd_prologue(const pd_config* cfg, const double* tau, const double* omega, const double* leg_all, const double* f,
@@ -80,6 +80,7 @@ int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const 
         a.beam = beam; a.iso = iso; a.only_flagged = 0;
         a.omega_s = omega_s; a.wleg = wleg; a.s_s = s_s; a.colp = colp; a.pmu0 = pmu0; a.mu = mu_nodes; a.w = w_nodes;
         a.K = K; a.G = G; a.Bv = Bv; a.dth = dth; a.status = status;
+        a.nflagged = (workspace && workspace_bytes >= PD_WS_HEAD) ? static_cast<int32_t*>(workspace) : nullptr;
         if (int rc = pd_launch_stage_a(a, cfg->flags, ptab, pd_stream(stream))) return rc;
     }
     if (stages & PD_STAGE_BC) {
@@ -89,7 +90,10 @@ int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const 
         sb.taus = taus; sb.colp = colp; sb.bpos = bpos_s; sb.bneg = bneg_s; sb.mu = mu_nodes; sb.w = w_nodes;
         sb.bdrf_q = bdrf_q; sb.bdrf_q0 = bdrf_q0; sb.K = K; sb.G = G; sb.Bv = Bv; sb.dth = dth; sb.C = C;
         sb.status = status;
-        if (int rc = pd_launch_stage_b(sb, cfg->flags, workspace, workspace_bytes, pd_stream(stream))) return rc;
+        if (!workspace || workspace_bytes < PD_WS_HEAD) return -20;
+        if (int rc = pd_launch_stage_b(sb, cfg->flags, static_cast<char*>(workspace) + PD_WS_HEAD, workspace_bytes - PD_WS_HEAD,
+                                       pd_stream(stream)))
+            return rc;
     }
     return 0;
 }

@@ -6,6 +6,7 @@
 template <int LANES, int NC>
 __global__ void k_stage_a(PdStageA a, const double* __restrict__ ptab, int items_per_cta, int item_doubles, int reps) {
     extern __shared__ double smem[];
+    if (a.only_flagged && a.nflagged && *a.nflagged == 0) return;  // nothing was handed back (the usual case)
     const int m = blockIdx.y;
     const int n = NC > 0 ? NC : a.N, nm = a.NLeg - m;
     double* Q = smem;  // [nm][n] scaled Legendre table of this mode (built when the CTA has work)
@@ -73,7 +74,10 @@ __global__ void __launch_bounds__(PD_SYM_THREADS, ((N <= 4) ? 4 : 2) * (128 / PD
     if (it >= (long)a.B * a.L) return;
     const int b = (int)(it / a.L), l = (int)(it % a.L);
     const bool done = pd_stage_a_sym_item<N>(a, b, m, l, QQ, Qs, park + threadIdx.x, blockDim.x);
-    if (!done) a.K[(((long)b * a.NF + m) * a.L + l) * N] = __longlong_as_double(0x7ff8000000000000LL);
+    if (!done) {
+        a.K[(((long)b * a.NF + m) * a.L + l) * N] = __longlong_as_double(0x7ff8000000000000LL);
+        if (a.nflagged) atomicAdd(a.nflagged, 1);
+    }
 }
 
 // eight lanes per item, symmetric (Cholesky + two-sided Jacobi) path, N = 16
@@ -109,8 +113,10 @@ __global__ void __launch_bounds__(PD_J16_THREADS, PD_J16_MINB) k_stage_a_j16(
     if (!valid) it = items - 1;  // padding lanes of the last CTA run along (the warp's shuffles need them) without storing
     const int b = (int)(it / a.L), l = (int)(it % a.L);
     const bool done = pd_stage_a_j16_item(a, b, m, l, valid, Qs, tab, scratch + (long)(threadIdx.x >> 3) * PdJ16::ITEM);
-    if (valid && !done && (threadIdx.x & 7) == 0)
+    if (valid && !done && (threadIdx.x & 7) == 0) {
         a.K[(((long)b * a.NF + m) * a.L + l) * 16] = __longlong_as_double(0x7ff8000000000000LL);
+        if (a.nflagged) atomicAdd(a.nflagged, 1);
+    }
 }
 
 static int launch_j16(const PdStageA& a, const double* ptab, cudaStream_t st) {
@@ -139,6 +145,10 @@ static int launch_sym(const PdStageA& a, const double* ptab, cudaStream_t st) {
 int pd_launch_stage_a(const PdStageA& a_in, int flags, const double* ptab, cudaStream_t st) {
     PdStageA a = a_in;
     a.only_flagged = 0;
+    if (a.nflagged) {
+        cudaError_t e = cudaMemsetAsync(a.nflagged, 0, sizeof(int32_t), st);
+        if (e != cudaSuccess) return (int)e;
+    }
     if ((a.N == 4 || a.N == 8 || (a.N == 16 && a.NLeg <= 32)) && !(flags & PD_FLAG_GENERIC_KERNELS)) {  // symmetric fast path first; the general kernel then only redoes flagged items
         const int rc = (a.N == 4) ? launch_sym<4>(a, ptab, st) : (a.N == 8) ? launch_sym<8>(a, ptab, st) : launch_j16(a, ptab, st);
         if (rc) return rc;

@@ -10,6 +10,7 @@
 #define PD_NUM_SMS 148               // B200
 #define PD_SMEM_BUDGET (200 * 1024)  // per-SM shared memory we plan residency against
 #define PD_SMEM_MAX_CTA (227 * 1024)
+#define PD_WS_HEAD 256               // first bytes of the caller's workspace: counter of eigen items handed to the general kernel
 
 static inline int pd_lanes_for(int n) {
     int l = 1;

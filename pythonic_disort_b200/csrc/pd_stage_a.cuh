@@ -18,6 +18,7 @@ struct PdStageA {
     int B, L, N, NLeg, NF, Ns;
     int beam, iso;
     int only_flagged;       // recompute only items whose K[item][0] is NaN (fallback pass after the symmetric kernel)
+    int32_t* nflagged;      // device counter of such items (null: unknown); the fallback pass returns at once if it is 0
     const double* omega_s;  // [B][L]
     const double* wleg;     // [B][L][NLeg]
     const double* s_s;      // [B][L][Ns]

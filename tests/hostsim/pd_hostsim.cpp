@@ -74,7 +74,7 @@ int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const 
     a.B = cfg->B; a.L = cfg->L; a.N = N; a.NLeg = cfg->NLeg; a.NF = cfg->NFourier; a.Ns = cfg->Nscoeffs;
     a.beam = (cfg->flags & PD_FLAG_BEAM) != 0; a.iso = (cfg->flags & PD_FLAG_ISO) != 0;
     a.omega_s = omega_s; a.wleg = wleg; a.s_s = s_s; a.colp = colp; a.pmu0 = pmu0; a.mu = mu_nodes; a.w = w_nodes;
-    a.K = K; a.G = G; a.Bv = Bv; a.dth = dth; a.status = status; a.only_flagged = 0;
+    a.K = K; a.G = G; a.Bv = Bv; a.dth = dth; a.status = status; a.only_flagged = 0; a.nflagged = nullptr;
     SerialGroup g;
     double* sm = (double*)malloc(sizeof(double) * (pd_stage_a_item_doubles(N, cfg->NLeg) + 16));
     double* Q = (double*)malloc(sizeof(double) * cfg->NLeg * N);
