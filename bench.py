@@ -354,7 +354,7 @@ class Bench:
         bytes_k = {"solve_eigen": item * (NQuad + 1) * 8 + item * (2 * N * N + N + 2 * N) * 8,
                    "solve_bc": item * (2 * N * N + N + 2 * N) * 8 + item * 2 * N * 8}[dom]
         kname = {"solve_eigen": "k_stage_a_sym" if N in (4, 8) else "k_stage_a_j16" if N == 16 else "k_stage_a",
-                 "solve_bc": "k_stage_b_add" if N in (2, 4, 8, 16) else "k_stage_b"}[dom]
+                 "solve_bc": "k_stage_b_tps" if N in (2, 4) else "k_stage_b_add" if N in (8, 16) else "k_stage_b"}[dom]
         per_col = self.traffic.get(workload, {}).get(kname)
         peak = self.fp64_peak
         roofline = {"kernel": kname, "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -405,7 +405,7 @@ def run_gpu(args):
                      not args.no_cpu, pool)
     others = {}
     if args.workload == "sw" and not args.no_others and not args.columns:
-        plan = [("lw", True, 2, 1), ("ha", True, 1, 1), ("sw_flux", False, 2, 1), ("tp1", False, 3, 2), ("tp9c", False, 3, 2)]
+        plan = [("lw", True, 3, 3), ("ha", True, 1, 3), ("sw_flux", False, 3, 3), ("tp1", False, 3, 3), ("tp9c", False, 3, 3)]
         for name, strong_o, st, wu in plan:
             r = bench.run(name, st, wu, strong_o, 0, 0, min(args.cpu_seconds, 5.0), not args.no_cpu, pool)
             keep = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "scaling", "e2e", "cpu_baseline", "gpu_launches")}

@@ -26,6 +26,17 @@ PD_HD int pd_locate(const double* tau_col, int L, double t) {
     return lo;
 }
 
+// The same index found by a lane group together: the lanes count the boundaries above the point, every load is
+// independent (one memory latency instead of log2(L) dependent ones -- the evaluation kernels are latency bound).
+template <class Grp>
+PD_HD int pd_locate_group(const Grp& g, const double* tau_col, int L, double t) {
+    int cnt = 0;
+    for (int j = g.lane(); j < L - 1; j += Grp::size) cnt += (tau_col[j] < t) ? 1 : 0;  // strictly increasing tau
+    double tot = 0.0;
+    for (int s = 0; s < Grp::size; ++s) tot += g.shfl((double)cnt, s);
+    return (int)tot;
+}
+
 // scaled optical depth of a query point (:189-195); dm = column uses delta-M scaling
 PD_HD double pd_scaled_tau(const PdEval& a, int b, int l, double t) {
     const double dm = a.st.colp[(long)b * PD_NCOLP + PD_COL_DM];
@@ -124,7 +135,7 @@ PD_HD void pd_flux_point(const Grp& g, const PdEval& a, int b, int t, double* sm
                          double* Fdir) {
     const int n = a.N;
     const double tq = a.tau_q[(long)b * a.ntau + t];
-    const int l = pd_locate(a.st.tau + (long)b * a.L, a.L, tq);
+    const int l = pd_locate_group(g, a.st.tau + (long)b * a.L, a.L, tq);
     const double ts = pd_scaled_tau(a, b, l, tq);
     double* ev = sm;
     double* uv = sm + 2 * n;
@@ -163,7 +174,7 @@ template <class Grp, int NC = 0>
 PD_HD void pd_u0_point(const Grp& g, const PdEval& a, int b, int t, double* sm, double* u0, double* recl) {
     const int n = a.N, n2 = 2 * n;
     const double tq = a.tau_q[(long)b * a.ntau + t];
-    const int l = pd_locate(a.st.tau + (long)b * a.L, a.L, tq);
+    const int l = pd_locate_group(g, a.st.tau + (long)b * a.L, a.L, tq);
     const double ts = pd_scaled_tau(a, b, l, tq);
     double* ev = sm;
     double* uv = sm + n2;

@@ -41,7 +41,7 @@ __global__ void k_eval_u(PdEval a, const double* __restrict__ phi_q, int nphi, i
     double* ev = smem + (long)gi * group_doubles;
     double* um = ev + n2;
     const double tq = a.tau_q[pt];
-    const int l = pd_locate(a.st.tau + (long)b * a.L, a.L, tq);
+    const int l = pd_locate_group(g, a.st.tau + (long)b * a.L, a.L, tq);
     const double ts = pd_scaled_tau(a, b, l, tq);
     pd_all_modes_point<SubWarp<LANES>, NC>(g, a, b, l, ts, ev, um);
     const double* cp = a.st.colp + (long)b * PD_NCOLP;

@@ -30,10 +30,15 @@ def main():
                                                    "gpu__time_duration.sum"))
         per = result.setdefault(workload, {})
         meta = per.setdefault("_capture", {"columns": int(cols), "kernels": {}})
+        prologues = 0
         for r in rows[2:]:
             name = re.sub(r"[<(].*", "", r[inm].replace("void ", "")).strip()
             if name == "k_fp64_probe":   # bench.py's peak measurement, not part of the path
                 continue
+            if name == "k_prologue":     # one chunk = the launches from one prologue to the next
+                prologues += 1
+                if prologues > 1:
+                    break
             b = float(r[ir].replace(",", "")) * UNIT[units[ir]] + float(r[iw].replace(",", "")) * UNIT[units[iw]]
             per[name] = per.get(name, 0.0) + b / int(cols)
             k = meta["kernels"].setdefault(name, {"launches": 0, "dram_bytes": 0.0, "time_" + units[it]: 0.0})
