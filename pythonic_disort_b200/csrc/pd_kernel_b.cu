@@ -10,8 +10,10 @@
 #include "pd_stage_b_tps.cuh"
 
 template <int NC>
-__global__ void k_stage_b(PdStageB a, double* hist, long hist_doubles, int sys_doubles, const int32_t* only_flagged) {
+__global__ void k_stage_b(PdStageB a, double* hist, long hist_doubles, int sys_doubles, const int32_t* only_flagged,
+                          const int32_t* nflagged) {
     extern __shared__ double smem[];
+    if (only_flagged && nflagged && *nflagged == 0) return;  // the first kernel handed nothing back (the usual case)
     const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5;
     const long slot = (long)blockIdx.x * wpb + w;
     const long nslots = (long)gridDim.x * wpb;
@@ -45,7 +47,8 @@ struct AddCfg {
 };
 
 template <int N>
-__global__ void __launch_bounds__(AddCfg<N>::THREADS, AddCfg<N>::MINB) k_stage_b_add(PdStageB a, double* hist, long hist_doubles, int32_t* sysflag) {
+__global__ void __launch_bounds__(AddCfg<N>::THREADS, AddCfg<N>::MINB) k_stage_b_add(PdStageB a, double* hist, long hist_doubles, int32_t* sysflag,
+                                                                                     int32_t* nflagged) {
     extern __shared__ double smem[];
     using Cf = AddCfg<N>;
     const int gi = threadIdx.x / Cf::LS;
@@ -57,7 +60,10 @@ __global__ void __launch_bounds__(AddCfg<N>::THREADS, AddCfg<N>::MINB) k_stage_b
     const long nsys = (long)a.B * a.NF;
     for (long s = slot; s < nsys; s += nslots) {
         const bool ok = pd_stage_b_add<SubWarp<Cf::LS>, N>(g, a, (int)(s / a.NF), (int)(s % a.NF), sm, h);
-        if (!ok && g.lane() == 0) sysflag[s] = 1;  // redone by k_stage_b
+        if (!ok && g.lane() == 0) {  // redone by k_stage_b
+            sysflag[s] = 1;
+            atomicAdd(nflagged, 1);
+        }
     }
 }
 
@@ -68,13 +74,17 @@ __global__ void __launch_bounds__(AddCfg<N>::THREADS, AddCfg<N>::MINB) k_stage_b
 #define PD_TPS_MINB 4
 #endif
 template <int N>
-__global__ void __launch_bounds__(PD_TPS_THREADS, PD_TPS_MINB) k_stage_b_tps(PdStageB a, double* hist, int32_t* sysflag) {
+__global__ void __launch_bounds__(PD_TPS_THREADS, PD_TPS_MINB) k_stage_b_tps(PdStageB a, double* hist, int32_t* sysflag,
+                                                                             int32_t* nflagged) {
     const long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long nslots = (long)gridDim.x * blockDim.x;
     const long nsys = (long)a.B * a.NF;
     for (long s = slot; s < nsys; s += nslots) {
         const bool ok = pd_stage_b_tps<N>(a, (int)(s / a.NF), (int)(s % a.NF), hist + slot, nslots);
-        if (!ok) sysflag[s] = 1;  // redone by k_stage_b
+        if (!ok) {  // redone by k_stage_b
+            sysflag[s] = 1;
+            atomicAdd(nflagged, 1);
+        }
     }
 }
 
@@ -95,7 +105,7 @@ static void plan_tps(StageBPlan& p, long nsys, int L) {
 
 template <int N>
 static int launch_tps(const PdStageB& a, const StageBPlan& p, double* hist, int32_t* sysflag, cudaStream_t st) {
-    k_stage_b_tps<N><<<p.add_blocks, PD_TPS_THREADS, 0, st>>>(a, hist, sysflag);
+    k_stage_b_tps<N><<<p.add_blocks, PD_TPS_THREADS, 0, st>>>(a, hist, sysflag, sysflag + (p.flag_bytes - 256) / 4);
     return (int)cudaGetLastError();
 }
 
@@ -121,7 +131,7 @@ static int launch_add(const PdStageB& a, const StageBPlan& p, double* hist, int3
     using Cf = AddCfg<N>;
     cudaError_t e = cudaFuncSetAttribute(k_stage_b_add<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cf::SMEM);
     if (e != cudaSuccess) return (int)e;
-    k_stage_b_add<N><<<p.add_blocks, Cf::THREADS, Cf::SMEM, st>>>(a, hist, p.add_hist, sysflag);
+    k_stage_b_add<N><<<p.add_blocks, Cf::THREADS, Cf::SMEM, st>>>(a, hist, p.add_hist, sysflag, sysflag + (p.flag_bytes - 256) / 4);
     return (int)cudaGetLastError();
 }
 
@@ -137,7 +147,7 @@ StageBPlan pd_plan_stage_b(int B, int NF, int N, int L, int flags) {
             case 8: plan_add<8>(p, nsys, L); break;
             default: plan_add<16>(p, nsys, L); break;
         }
-        p.flag_bytes = ((size_t)nsys * sizeof(int32_t) + 255) & ~(size_t)255;
+        p.flag_bytes = (((size_t)nsys * sizeof(int32_t) + 255) & ~(size_t)255) + 256;  // + the counter of flagged systems
     }
     // pivoted band solver: the whole job, or a small grid for the systems the first kernel flags
     p.sys_doubles = (pd_stage_b_doubles(N) + 1) & ~1;
@@ -160,9 +170,10 @@ StageBPlan pd_plan_stage_b(int B, int NF, int N, int L, int flags) {
 
 template <int NC>
 static int launch_b(const PdStageB& a, const StageBPlan& pb, double* hist, const int32_t* only_flagged, cudaStream_t st) {
+    const int32_t* nflagged = only_flagged ? only_flagged + (pb.flag_bytes - 256) / 4 : nullptr;
     cudaError_t e = cudaFuncSetAttribute(k_stage_b<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb.smem);
     if (e != cudaSuccess) return (int)e;
-    k_stage_b<NC><<<pb.blocks, pb.wpb * 32, pb.smem, st>>>(a, hist, pb.hist_doubles, pb.sys_doubles, only_flagged);
+    k_stage_b<NC><<<pb.blocks, pb.wpb * 32, pb.smem, st>>>(a, hist, pb.hist_doubles, pb.sys_doubles, only_flagged, nflagged);
     return (int)cudaGetLastError();
 }
 
