@@ -75,6 +75,30 @@ def algorithmic_flops(L, NQuad, NLeg, NF, beam, thermal, nlev, nphi):
     return dict(eigen_stage=setup + eig + part, bc_stage=bc, eval=ev, total=setup + eig + part + bc + ev)
 
 
+L2_POLICY = ("inputs and solved state of a step are far larger than L2 (>= 1 GB per chunk except tp1/tp9c, whose "
+             "4096-column state is 50-90 MB against 126 MB of L2: those two are L2-warm numbers); no explicit flush")
+
+
+def workload_config(workload, cols_total, per_gpu, chunk, chunk_e2e):
+    """The `config` object of a bench line: identical for the GPU arm and the `--impl reference` arm of one workload."""
+    return {"workload": workload, "description": WORKLOADS[workload]["desc"], "columns_total": cols_total,
+            "columns_per_gpu": per_gpu, "chunk_columns": chunk, "chunk_columns_e2e": chunk_e2e,
+            "seed": "pythonic_disort_b200/synthetic.py", "l2_policy": L2_POLICY}
+
+
+def chunk_sizes(workload, per_gpu, chunk=0):
+    """(columns per pydisort() call of the device-resident arm, of the host pipeline): the first as many as the solved
+    state allows, the second at least six chunks per ensemble (ensemble.default_chunk); --chunk overrides both."""
+    from pythonic_disort_b200 import ensemble
+    wl = WORKLOADS[workload]
+    L, NQuad = SHAPES[wl["ens"]]
+    NF = 1 if wl.get("only_flux") or wl["ens"] == "lw" else NQuad
+    if chunk > 0:
+        return min(chunk, per_gpu), min(chunk, per_gpu)
+    return (min(ensemble.default_chunk(per_gpu, L, NQuad, NF, pipeline=False), per_gpu),
+            min(ensemble.default_chunk(per_gpu, L, NQuad, NF), per_gpu))
+
+
 def make_inputs(name, ncol, first, only_flux=False):
     from pythonic_disort_b200 import synthetic
     ens = synthetic.make(name, ncol, first)
@@ -257,9 +281,7 @@ class Bench:
         N = NQuad // 2
         NF = 1 if (only_flux or ens["kwargs"].get("only_flux")) else NQuad
         want_u = "u" in ens["outputs"]
-        if chunk <= 0:
-            chunk = ensemble.default_chunk(B, L, NQuad, NF)
-        chunk = min(chunk, B)
+        chunk, chunk_e2e = chunk_sizes(workload, B, chunk)
         phi = ens["phi_eval"] if want_u else None
         mu_user = ens.get("mu_user") if want_u else None
         outputs = ("flux_up", "flux_down") + (("u",) if want_u else ())
@@ -318,7 +340,7 @@ class Bench:
 
         def step_e2e(k):
             cur = ensemble.solve_ensemble(*host_args, tau=host_tau, phi=phi, mu=mu_user, outputs=outputs,
-                                          chunk=chunk, out=results[k % 2], wait=False, **host_kw)
+                                          chunk=chunk_e2e, out=results[k % 2], wait=False, **host_kw)
             prev = results[(k + 1) % 2]
             if prev is not None:
                 prev.wait()   # step k - 1 has reached the host (its deferred checks are raised here)
@@ -382,11 +404,7 @@ class Bench:
         return {
             "metric": wl.get("metric", f"columns/s ({workload})"), "value": value, "unit": "columns/s",
             "ms_per_step": ms_step, "steps": steps, "warmup": warmup, "scaling": "strong" if strong else "weak",
-            "config": {"workload": workload, "description": wl["desc"], "columns_total": cols_total,
-                       "columns_per_gpu": B, "chunk_columns": chunk, "seed": "pythonic_disort_b200/synthetic.py",
-                       "l2_policy": "inputs and solved state of a step are far larger than L2 (>= 1 GB per chunk "
-                       "except tp1/tp9c, whose 4096-column state is 50-90 MB against 126 MB of L2: those two are "
-                       "L2-warm numbers); no explicit flush"},
+            "config": workload_config(workload, cols_total, B, chunk, chunk_e2e),
             "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "pythonic_disort_b200.ensemble.solve_ensemble"},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
@@ -409,7 +427,8 @@ def run_gpu(args):
         for name, strong_o, st, wu in plan:
             r = bench.run(name, st, wu, strong_o, 0, 0, min(args.cpu_seconds, 5.0), not args.no_cpu, pool)
             keep = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "scaling", "e2e", "cpu_baseline", "gpu_launches")}
-            keep["config"] = {k: r["config"][k] for k in ("description", "columns_total", "columns_per_gpu", "chunk_columns")}
+            keep["config"] = {k: r["config"][k] for k in ("description", "columns_total", "columns_per_gpu", "chunk_columns",
+                                                           "chunk_columns_e2e")}
             rf = r["roofline"]
             keep["roofline"] = {k: rf[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic",
                                                    "traffic_bytes_per_column", "kernel_ms_per_step_all")}
@@ -425,7 +444,7 @@ def run_gpu(args):
         if others:
             line["other_workloads"] = others
         if bench.cores:
-            line["config"]["cpu_affinity"] = f"{len(bench.cores)} cores local to the GPU (NVML)"
+            line["cpu_affinity"] = f"{len(bench.cores)} cores local to the GPU (NVML)"
         print(json.dumps(line))
     if bench.world > 1:
         bench.dist.destroy_process_group()
@@ -444,14 +463,14 @@ def run_reference(args):
     value = float(np.median(vals[1:])) if len(vals) > 1 else vals[0]
     total = args.columns or wl["columns"]
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    strong = args.scaling == "strong"
+    per_gpu = -(-total // world) if strong else total   # what the GPU arm of the same command gives every rank
     line = {
         "impl": "reference", "metric": wl.get("metric", f"columns/s ({args.workload})"),
         "value": value, "unit": "columns/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "description": wl["desc"],
-                   "columns_total": total * (1 if args.scaling == "strong" else world), "columns_per_gpu": None,
-                   "chunk_columns": None, "seed": "pythonic_disort_b200/synthetic.py"},
+        "config": workload_config(args.workload, total * (1 if strong else world), per_gpu, *chunk_sizes(args.workload, per_gpu, args.chunk)),
         "cpu_baseline": {"value": value, "unit": "columns/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

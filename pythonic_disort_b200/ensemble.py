@@ -54,14 +54,14 @@ def pinned(x):
     return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).pin_memory()
 
 
-def default_chunk(B, L, NQuad, NFourier):
+def default_chunk(B, L, NQuad, NFourier, pipeline=True):
     """Columns per pydisort() call: solved state of a chunk (K, G, Bv, C) below ~24 GB, a multiple of 1024 (one that
-    divides B if there is one), and at least six chunks per ensemble so that the first upload and the last download
-    are small next to the rest."""
+    divides B if there is one) and, for the host pipeline (``pipeline=True``), at least six chunks per ensemble so that
+    the first upload and the last download are small next to the rest."""
     N = NQuad // 2
     per_col = NFourier * L * (2 * N * N + 5 * N) * 8
     limit = max(1024, min(int(24e9 / per_col), 1 << 17) // 1024 * 1024)
-    if B >= 6 * 1024:
+    if pipeline and B >= 6 * 1024:
         limit = min(limit, max(1024, (B // 6) // 1024 * 1024))
     if B <= limit:
         return max(1, B)
