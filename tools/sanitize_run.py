@@ -4,8 +4,11 @@
     compute-sanitizer --tool memcheck  python tools/sanitize_run.py
     compute-sanitizer --tool racecheck python tools/sanitize_run.py
 
-Covers the input helpers (Planck band integrals, s_poly coefficients, Hapke Fourier modes), SW (N = 8: symmetric stage A, tensor-core stage B, u + tabulated NT, interpolate), LW (N = 4: three-row
-register stage B, thermal source) and HA (N = 16: general stage A, tensor-core stage B, BDRF surface)."""
+Covers the input helpers (Planck band integrals, s_poly coefficients, Hapke Fourier modes), SW (N = 8: one-thread
+symmetric eigen stage, lane-group elimination over interface radiances, u + tabulated NT, interpolate), LW (N = 4:
+one-thread-per-system boundary-condition stage, thermal source), HA (N = 16: eight-lane symmetric eigen stage with its
+shuffles and shared-memory hand-offs, 16-lane boundary-condition stage, BDRF surface) and the size-generic kernels
+(general eigen stage, pivoted band solver) through the PD_FLAG_GENERIC_KERNELS test bit."""
 import os
 import sys
 import warnings
@@ -31,6 +34,14 @@ for name, ncol in (("sw", 6), ("lw", 20), ("ha", 2)):
         chk += float(np.sum(u)) + float(np.sum(um))
     assert np.isfinite(chk), name
     print(name, "ok", chk)
+from pythonic_disort_b200 import _lib  # noqa: E402
+
+for name, ncol in (("sw", 2), ("tp9c", 1)):
+    ens = synthetic.make(name, ncol)
+    out = pd.pydisort(*ens["args"], _kernel_flags=_lib.PD_FLAG_GENERIC_KERNELS, **ens["kwargs"])
+    chk = float(np.sum(out[1](ens["tau_eval"]))) + float(np.sum(out[4](ens["tau_eval"], ens["phi_eval"])))
+    assert np.isfinite(chk), name
+    print(name, "generic kernels ok", chk)
 import torch  # noqa: E402
 
 T = torch.linspace(0.0, 320.0, 257, device="cuda", dtype=torch.float64)
