@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(PD_J16_THREADS, PD_J16_MINB) k_stage_a_j16(
     extern __shared__ double smem[];
     const int m = blockIdx.y, nm = a.NLeg - m;
     double* Qs = smem;            // [nm][16]
-    double* tab = Qs + 32 * 16;   // 0.5 / sqrt(w mu), 1 / mu
-    double* scratch = tab + 32;
+    double* tab = Qs + 32 * 16;   // 0.5 / sqrt(w mu), 1 / mu, sqrt(w / mu)
+    double* scratch = tab + 48;
     for (int idx = threadIdx.x; idx < nm * 16; idx += blockDim.x) {
         const int i = idx & 15;
         Qs[idx] = ptab[((long)m * a.NLeg + m) * 16 + idx] * sqrt(a.w[i] / a.mu[i]);
@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(PD_J16_THREADS, PD_J16_MINB) k_stage_a_j16(
     if (threadIdx.x < 16) {
         tab[threadIdx.x] = 0.5 * pd_rsqrt(a.w[threadIdx.x] * a.mu[threadIdx.x]);
         tab[16 + threadIdx.x] = 1.0 / a.mu[threadIdx.x];
+        tab[32 + threadIdx.x] = sqrt(a.w[threadIdx.x] / a.mu[threadIdx.x]);
     }
     __syncthreads();
     const long items = (long)a.B * a.L;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(PD_J16_THREADS, PD_J16_MINB) k_stage_a_j16(
 
 static int launch_j16(const PdStageA& a, const double* ptab, cudaStream_t st) {
     const int ipc = PD_J16_THREADS / 8;
-    const size_t smem = (size_t)(32 * 16 + 32 + ipc * PdJ16::ITEM) * 8;
+    const size_t smem = (size_t)(32 * 16 + 48 + ipc * PdJ16::ITEM) * 8;
     cudaError_t e = cudaFuncSetAttribute(k_stage_a_j16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const long items = (long)a.B * a.L;

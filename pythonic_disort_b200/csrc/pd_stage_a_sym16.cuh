@@ -1,6 +1,6 @@
 // pd_stage_a_sym16.cuh -- stage A for N = 16 (NQuad = 32): EIGHT LANES per (column, mode, layer) item, matrices in
 // registers, fixed control flow (production path of the high-accuracy shape; pd_stage_a.cuh + pd_linalg.cuh stay the
-// general path and the fallback for flagged items and for the thermal mode-0 items).
+// general path and the fallback for flagged items).
 //
 // Same mathematics as pd_stage_a_sym.cuh (_solve_for_gen_and_part_sols.py:114-231 in the similarity-scaled basis):
 //     X' = -(alpha-beta)^,  S = -(alpha+beta)^ = L L^T,  T = L^T X' L,  T W = W diag(k^2),
@@ -143,7 +143,7 @@ __device__ __forceinline__ double pd_j16_sum8(double v) {
     return v;
 }
 
-// Qs: [nm][16] scaled Legendre table of this mode, tab: [0..15] 0.5 / sqrt(w mu), [16..31] 1 / mu (both shared by the
+// Qs: [nm][16] scaled Legendre table of this mode, tab: [0..15] 0.5 / sqrt(w mu), [16..31] 1 / mu, [32..47] sqrt(w / mu) (shared by the
 // CTA); sm: this item's scratch.  All 32 lanes of a warp must call this together (`store` = false for the padding
 // items of the last CTA).  Returns false if the general solver must redo the item.
 __device__ __forceinline__ bool pd_stage_a_j16_item(const PdStageA& a, int b, int m, int l, bool store, const double* Qs,
@@ -486,9 +486,82 @@ __device__ __forceinline__ bool pd_stage_a_j16_item(const PdStageA& a, int b, in
             pd_st2(Bout + 16 + 2 * lam, bba, bbb);
         }
     }
+    if (thermal) {  // mode 0 of a problem with an isotropic source (uniform over the CTA: the shuffles below are safe)
+        // y = -k V^T (D / mu) (the lane's two eigen indices), then for every power q of the source polynomial
+        //   t-+ = b_q(-+k) y,   d_q = G [t-; -t+]:  top = V^ (t- - t+) + U^ (t- + t+),  bottom = V^ (t- - t+) - U^ (t- + t+)
+        // (subroutines.py:783-862, as in pd_stage_a_sym.cuh); U^ column j = -Ua_j / k_j
+        const double* fsq = tab + 32;  // sqrt(w / mu)
+        double ya = 0.0, yb = 0.0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const double f = fsq[r];
+            ya = fma(Wa[r], f, ya);
+            yb = fma(Wb[r], f, yb);
+        }
+        ya *= -ka;
+        yb *= -kb;
+        const double* sc = a.s_s + ((long)b * a.L + l) * a.Ns;
+        double* dout = a.dth + ((long)b * a.L + l) * a.Ns * 32;
+        double m0, m1, d0, d1;
+        pd_ld2(rmu + 2 * lam, m0, m1);
+        pd_ld2(dinvs + 2 * lam, d0, d1);
+        for (int q = 0; q < a.Ns; ++q) {
+            // polynomial sums b_q(+k), b_q(-k) for the two eigen indices (active) and for k = 1 / mu_i (shortcut)
+            double bpa = 0.0, bna = 0.0, bpb = 0.0, bnb = 0.0, spa = 0.0, sna = 0.0, spb = 0.0, snb = 0.0;
+            double ratio = 1.0, pwa = kia, pwb = kib, pma = 1.0 / m0, pmb = 1.0 / m1;
+            for (int r = q; r < a.Ns; ++r) {
+                if (r > q) {
+                    ratio *= (double)r;
+                    pwa *= kia;
+                    pwb *= kib;
+                    pma *= 1.0 / m0;
+                    pmb *= 1.0 / m1;
+                }
+                const double c = sc[r] * ratio;
+                const bool odd = ((r - q) & 1) != 0;
+                bpa = fma(c, pwa, bpa);
+                bna = fma(c, odd ? pwa : -pwa, bna);
+                bpb = fma(c, pwb, bpb);
+                bnb = fma(c, odd ? pwb : -pwb, bnb);
+                spa = fma(c, pma, spa);
+                sna = fma(c, odd ? pma : -pma, sna);
+                spb = fma(c, pmb, spb);
+                snb = fma(c, odd ? pmb : -pmb, snb);
+            }
+            const double dma = (bna - bpa) * ya, sma = (bna + bpa) * ya, dmb = (bnb - bpb) * yb, smb = (bnb + bpb) * yb;
+            const double ua_s = -kia * sma, ub_s = -kib * smb;
+            double ta = 0.0, tb = 0.0, ba = 0.0, bb = 0.0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const double vv = pd_j16_sum8(fma(Wa[i], dma, Wb[i] * dmb));
+                const double uu = pd_j16_sum8(fma(Ua[i], ua_s, Ub[i] * ub_s));
+                if (i == 2 * lam) {
+                    ta = vv + uu;
+                    ba = vv - uu;
+                }
+                if (i == 2 * lam + 1) {
+                    tb = vv + uu;
+                    bb = vv - uu;
+                }
+            }
+            ta *= d0;  // dinvs carries the factor 1/2
+            ba *= d0;
+            tb *= d1;
+            bb *= d1;
+            if (!active) {  // shortcut layer: y = -1/mu, k = 1/mu:  top = b_q(+k) / mu, bottom = -b_q(-k) / mu
+                ta = spa * m0;
+                tb = spb * m1;
+                ba = -sna * m0;
+                bb = -snb * m1;
+            }
+            if (store) {
+                pd_st2(dout + q * 32 + 2 * lam, ta, tb);
+                pd_st2(dout + q * 32 + 16 + 2 * lam, ba, bb);
+            }
+        }
+    }
     __syncwarp();
-    if (!active) return !thermal;  // the shortcut needs no decomposition; thermal items go to the general solver
-    return ok && !thermal;
+    return !active || ok;  // the shortcut needs no decomposition
 }
 
 #endif  // __CUDACC__
