@@ -50,8 +50,18 @@ PD_HD double pd_scaled_tau(const PdEval& a, int b, int l, double t) {
 
 // u^m at one point into uv[2n] (shared); ev[2n] is scratch.  Includes the beam
 // and (m = 0) thermal particular solutions; NOT multiplied by rescale_factor.
+// beam attenuation factor of a query point: exp(-tau* / mu0) (its tau-antiderivative if a.anti), 0 without a beam
+PD_HD double pd_beam_factor(const PdEval& a, int b, int l, double ts) {
+    if (!(a.beam && a.st.colp[(long)b * PD_NCOLP + PD_COL_I0] > 0.0)) return 0.0;
+    const double mu0 = a.st.colp[(long)b * PD_NCOLP + PD_COL_MU0];
+    double eb = exp(-ts / mu0);
+    if (a.anti) eb /= -(a.st.scale_tau[(long)b * a.L + l] / mu0);
+    return eb;
+}
+
+// `eb` = pd_beam_factor of the point (the same for every mode: callers that loop over the modes compute it once)
 template <class Grp, int NC = 0>
-PD_HD void pd_mode_at(const Grp& g, const PdEval& a, int b, int m, int l, double ts, double* ev, double* uv) {
+PD_HD void pd_mode_at(const Grp& g, const PdEval& a, int b, int m, int l, double ts, double eb, double* ev, double* uv) {
     const int lane = g.lane();
     const int n = NC > 0 ? NC : a.N, n2 = 2 * n;
     const long item = ((long)b * a.NF + m) * a.L + l;
@@ -73,13 +83,7 @@ PD_HD void pd_mode_at(const Grp& g, const PdEval& a, int b, int m, int l, double
         ev[n + j] = ep;
     }
     g.sync();
-    double eb = 0.0;
     const bool beam = a.beam && a.st.colp[(long)b * PD_NCOLP + PD_COL_I0] > 0.0;
-    if (beam) {
-        const double mu0 = a.st.colp[(long)b * PD_NCOLP + PD_COL_MU0];
-        eb = exp(-ts / mu0);
-        if (a.anti) eb /= -(sc / mu0);
-    }
     const double* Bv = beam ? a.st.Bv + item * n2 : nullptr;
     const double* dth = (a.iso && m == 0) ? a.st.dth + ((long)b * a.L + l) * a.Ns * n2 : nullptr;
     for (int i = lane; i < n; i += Grp::size) {
@@ -141,7 +145,7 @@ PD_HD void pd_flux_point(const Grp& g, const PdEval& a, int b, int t, double* sm
     const double ts = pd_scaled_tau(a, b, l, tq);
     double* ev = sm;
     double* uv = sm + 2 * n;
-    pd_mode_at<Grp, NC>(g, a, b, 0, l, ts, ev, uv);
+    pd_mode_at<Grp, NC>(g, a, b, 0, l, ts, pd_beam_factor(a, b, l, ts), ev, uv);
     if (g.lane() == 0) {
         double up = 0.0, dn = 0.0;
         for (int i = 0; i < n; ++i) {
@@ -180,7 +184,7 @@ PD_HD void pd_u0_point(const Grp& g, const PdEval& a, int b, int t, double* sm, 
     const double ts = pd_scaled_tau(a, b, l, tq);
     double* ev = sm;
     double* uv = sm + n2;
-    pd_mode_at<Grp, NC>(g, a, b, 0, l, ts, ev, uv);
+    pd_mode_at<Grp, NC>(g, a, b, 0, l, ts, pd_beam_factor(a, b, l, ts), ev, uv);
     const double* cp = a.st.colp + (long)b * PD_NCOLP;
     const double resc = cp[PD_COL_RESCALE];
     for (int i = g.lane(); i < n2; i += Grp::size) u0[((long)b * n2 + i) * a.ntau + t] = resc * uv[i];
@@ -203,7 +207,8 @@ PD_HD void pd_u0_point(const Grp& g, const PdEval& a, int b, int t, double* sm, 
 // all Fourier modes at one point into um[NF][2n] (shared); ev: 2n scratch
 template <class Grp, int NC = 0>
 PD_HD void pd_all_modes_point(const Grp& g, const PdEval& a, int b, int l, double ts, double* ev, double* um) {
-    for (int m = 0; m < a.NF; ++m) pd_mode_at<Grp, NC>(g, a, b, m, l, ts, ev, um + m * 2 * a.N);
+    const double eb = pd_beam_factor(a, b, l, ts);
+    for (int m = 0; m < a.NF; ++m) pd_mode_at<Grp, NC>(g, a, b, m, l, ts, eb, ev, um + m * 2 * a.N);
 }
 
 // sum_m um[m * stride] cos(m dphi)  (:256-260).  cos(m dphi) by the Chebyshev recurrence

@@ -87,11 +87,9 @@ __global__ void __launch_bounds__(PD_SYM_THREADS, ((N <= 4) ? 4 : 2) * (128 / PD
 #ifndef PD_J16_MINB
 #define PD_J16_MINB 4
 #endif
-#ifdef PD_J16_MAXREG
-__global__ void __maxnreg__(PD_J16_MAXREG) k_stage_a_j16(
-#else
+// 252 registers without spills at four CTAs of 64 threads per SM; capping at 168 / 200 registers for five or six CTAs
+// spills and is slower (measured 79 against 84 / 133 ms per 2,048 HA columns)
 __global__ void __launch_bounds__(PD_J16_THREADS, PD_J16_MINB) k_stage_a_j16(
-#endif
     PdStageA a, const double* __restrict__ ptab) {
     extern __shared__ double smem[];
     const int m = blockIdx.y, nm = a.NLeg - m;
