@@ -116,8 +116,13 @@ int pd_prologue(const pd_config* cfg,
  *      ptab[NFourier][NLeg][N]  normalised P~_l^m(mu_i), zero for l < m;
  *      bdrf_q[(B)][NBDRF][N][N] q^m(mu_i, mu_j); bdrf_q0[(B)][NBDRF][N] q^m(mu_i, mu0)
  * out: K  [B][NFourier][L][N]      positive eigenvalues k (K_collect = [-k, +k])
- *      G  [B][NFourier][L][2][N][N] the two distinct blocks of G_collect:
- *                                   G[0] = G[:N,:N] = G[N:,N:],  G[1] = G[:N,N:] = G[N:,:N]
+ *      G  ceil(B*NFourier*L / 32) * 32 items of 2*N*N doubles: the two distinct blocks of G_collect per
+ *                                   (column, mode, layer) item = (b * NFourier + m) * L + l,
+ *                                   block 0 = G[:N,:N] = G[N:,N:],  block 1 = G[:N,N:] = G[N:,:N];
+ *                                   element e = block*N*N + row*N + col of an item lives at (doubles)
+ *                                     item * 2*N*N + e                                          (NQuad != 16)
+ *                                     (item/32) * 32*2*N*N + (e/4)*128 + (item%32)*4 + e%4     (NQuad == 16:
+ *                                   groups of 32 items interleaved by 32-byte sectors, see pd_common.cuh)
  *      Bv [B][NFourier][L][2N]     beam particular solution (B_collect)
  *      dth[B][L][Ns][2N]           thermal particular solution, coefficient of tau*^q
  *      C  [B][NFourier][L][2N]     boundary-condition coefficients (GC_collect = G * C)

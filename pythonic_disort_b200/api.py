@@ -688,7 +688,9 @@ def pydisort(
     _mark("prologue", dev)
 
     sol.K = new(B, NFourier, L, N)
-    sol.G = new(B, NFourier, L, 2, N, N)
+    # the two distinct N x N blocks of every (column, mode, layer) item, sector-interleaved over groups of 32 items
+    # (include/pydisort_b200.h, "layout of G"): a flat buffer of ceil(items / 32) * 32 items
+    sol.G = new(-(-(B * NFourier * L) // 32) * 32 * 2 * N * N)
     sol.Bv = new(B, NFourier, L, NQuad) if beam else None
     sol.dth = new(B, L, Ns, NQuad) if Ns > 0 else None
     sol.C = new(B, NFourier, L, NQuad)

@@ -88,7 +88,7 @@ int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const 
         sb.B = cfg->B; sb.L = cfg->L; sb.N = N; sb.NF = cfg->NFourier; sb.Ns = cfg->Nscoeffs; sb.NBDRF = cfg->NBDRF;
         sb.NFb = cfg->NFb; sb.beam = beam; sb.iso = iso; sb.bdrf_percol = (cfg->flags & PD_FLAG_BDRF_PERCOL) != 0;
         sb.taus = taus; sb.colp = colp; sb.bpos = bpos_s; sb.bneg = bneg_s; sb.mu = mu_nodes; sb.w = w_nodes;
-        sb.bdrf_q = bdrf_q; sb.bdrf_q0 = bdrf_q0; sb.K = K; sb.G = G; sb.Bv = Bv; sb.dth = dth; sb.C = C;
+        sb.bdrf_q = bdrf_q; sb.bdrf_q0 = bdrf_q0; sb.K = K; sb.G = G; sb.RT = nullptr; sb.Bv = Bv; sb.dth = dth; sb.C = C;
         sb.status = status;
         if (!workspace || workspace_bytes < PD_WS_HEAD) return -20;
         if (int rc = pd_launch_stage_b(sb, cfg->flags, static_cast<char*>(workspace) + PD_WS_HEAD, workspace_bytes - PD_WS_HEAD,

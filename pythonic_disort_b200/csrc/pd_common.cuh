@@ -57,6 +57,24 @@ __device__ __forceinline__ void pd_cp_async_wait_all() {
 }
 #endif
 
+// Layout of G in HBM.  An item = the two N x N blocks [Gp | Gm] of one (column, mode, layer), 2 N^2 doubles, element
+// e = block * N^2 + row * N + column; item index = (column * NFourier + mode) * L + layer.
+//   N != 8: items one after the other, offset(item, e) = item * 2N^2 + e.
+//   N == 8: groups of 32 consecutive items, sector-interleaved -- the 32-byte chunk c (elements 4c .. 4c+3) of the 32
+//           items of a group lie next to each other,
+//               offset(item, e) = (item / 32) * 32 * 2N^2  +  (e / 4) * 128  +  (item % 32) * 4  +  e % 4.
+//           The one-thread-per-item kernels of this shape (the symmetric eigen stage, which writes G, and the layer-
+//           operator kernel, which reads it) then move whole contiguous kilobytes per warp instruction instead of 32
+//           sectors a kilobyte apart (eigen stage 80 -> 73 ms per SW step); lane-group readers still get full 32-byte
+//           sectors.  For the other shapes the readers are lane groups or one thread per SYSTEM, which lose 5-15 % on
+//           the scattered sectors (measured on LW and HA), so they keep the plain layout.
+// The buffer holds ceil(items / 32) * 32 items in either case.
+PD_HD bool pd_g_interleaved(int n) { return n == 8; }
+PD_HD long pd_g_base(long item, int n) {
+    return pd_g_interleaved(n) ? (item >> 5) * 32L * (2 * n * n) + (item & 31) * 4 : item * (2L * n * n);
+}
+PD_HD long pd_g_off(int e, int n) { return pd_g_interleaved(n) ? (long)(e >> 2) * 128 + (e & 3) : (long)e; }
+
 // padded leading dimension: odd, so that row- and column-wise lane access are both bank-conflict free
 PD_HD int pd_ld(int n) { return n | 1; }
 

@@ -66,8 +66,7 @@ PD_HD void pd_mode_at(const Grp& g, const PdEval& a, int b, int m, int l, double
     const int n = NC > 0 ? NC : a.N, n2 = 2 * n;
     const long item = ((long)b * a.NF + m) * a.L + l;
     const double* K = a.st.K + item * n;
-    const double* Gp = a.st.G + item * 2 * n * n;
-    const double* Gm = Gp + n * n;
+    const double* Gi = a.st.G + pd_g_base(item, n);  // layout: pd_common.cuh
     const double* C = a.st.C + item * n2;
     const double* taus = a.st.taus + (long)b * (a.L + 1);
     const double sc = a.st.scale_tau[(long)b * a.L + l];
@@ -92,8 +91,8 @@ PD_HD void pd_mode_at(const Grp& g, const PdEval& a, int b, int m, int l, double
 #pragma unroll
             for (int j = 0; j < (NC > 0 ? NC : 4); j += 4) {
                 double gp[4], gm[4];
-                pd_load4_stream(Gp + i * n + j, gp);
-                pd_load4_stream(Gm + i * n + j, gm);
+                pd_load4_stream(Gi + pd_g_off(i * n + j, n), gp);
+                pd_load4_stream(Gi + pd_g_off(n * n + i * n + j, n), gm);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     top = fma(gp[e], ev[j + e], top);
@@ -104,7 +103,7 @@ PD_HD void pd_mode_at(const Grp& g, const PdEval& a, int b, int m, int l, double
             }
         } else {
             for (int j = 0; j < n; ++j) {
-                const double gp = Gp[i * n + j], gm = Gm[i * n + j];
+                const double gp = Gi[pd_g_off(i * n + j, n)], gm = Gi[pd_g_off(n * n + i * n + j, n)];
                 top = fma(gp, ev[j], top);
                 top = fma(gm, ev[n + j], top);
                 bot = fma(gm, ev[j], bot);

@@ -1,11 +1,14 @@
 // pd_kernel_b.cu -- stage B kernels: the boundary-condition solve of every (column, Fourier mode) system.
 //   k_stage_b_add<N>  production path (N = 8, 16): a lane group per system, block elimination over the interface
 //                     radiances (pd_stage_b_add.cuh); persistent grid, one history slot per resident system
+//   k_layer_ops<8>    N = 8: reflection / transmission operators of every layer, one thread per (column, mode, layer)
+//                     item (pd_layer_ops.cuh); k_stage_b_add<8> then only runs the sweep over the layers
 //   k_stage_b_tps<N>  production path (N = 2, 4): the same elimination with ONE THREAD per system, every matrix in
 //                     registers (pd_stage_b_tps.cuh); persistent grid, history interleaved over the threads
 //   k_stage_b<NC>     size-generic pivoted band solver (pd_stage_b.cuh), one warp per system: any N, the
 //                     PD_FLAG_GENERIC_KERNELS test path, and the second pass over systems the first kernel flagged
 #include "pd_launch.h"
+#include "pd_layer_ops.cuh"
 #include "pd_stage_b_add.cuh"
 #include "pd_stage_b_tps.cuh"
 
@@ -46,7 +49,36 @@ struct AddCfg {
     static constexpr size_t SMEM = (size_t)F::SD * 8 * SPC;
 };
 
+#ifndef PD_OPS_THREADS
+#define PD_OPS_THREADS 128
+#endif
 template <int N>
+__global__ void __launch_bounds__(PD_OPS_THREADS, 2) k_layer_ops(PdStageB a, double* RT) {
+    extern __shared__ double smem[];
+    double* hD = smem;            // [N] sqrt(w mu) / 2
+    double* park = smem + 16;     // [NP][threads]
+    if (threadIdx.x < N) hD[threadIdx.x] = 0.5 * sqrt(a.w[threadIdx.x] * a.mu[threadIdx.x]);
+    __syncthreads();
+    const long item = (long)blockIdx.x * blockDim.x + threadIdx.x;  // (column, mode, layer)
+    if (item >= (long)a.B * a.NF * a.L) return;
+    const int l = (int)(item % a.L);
+    const int b = (int)(item / a.L / a.NF);
+    const double* ts = a.taus + (long)b * (a.L + 1) + l;
+    pd_layer_ops_item<N>(a.G + pd_g_base(item, N), a.K + item * N, ts[1] - ts[0], hD, RT + item * N * (N + 1),
+                         park + threadIdx.x, blockDim.x);
+}
+
+template <int N>
+static int launch_ops(const PdStageB& a, double* RT, cudaStream_t st) {
+    const size_t smem = (size_t)(16 + PdLayerOps<N>::NP * PD_OPS_THREADS) * 8;
+    cudaError_t e = cudaFuncSetAttribute(k_layer_ops<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const long items = (long)a.B * a.NF * a.L;
+    k_layer_ops<N><<<(unsigned)((items + PD_OPS_THREADS - 1) / PD_OPS_THREADS), PD_OPS_THREADS, smem, st>>>(a, RT);
+    return (int)cudaGetLastError();
+}
+
+template <int N, bool SPLIT>
 __global__ void __launch_bounds__(AddCfg<N>::THREADS, AddCfg<N>::MINB) k_stage_b_add(PdStageB a, double* hist, long hist_doubles, int32_t* sysflag,
                                                                                      int32_t* nflagged) {
     extern __shared__ double smem[];
@@ -59,7 +91,7 @@ __global__ void __launch_bounds__(AddCfg<N>::THREADS, AddCfg<N>::MINB) k_stage_b
     double* h = hist + slot * hist_doubles;
     const long nsys = (long)a.B * a.NF;
     for (long s = slot; s < nsys; s += nslots) {
-        const bool ok = pd_stage_b_add<SubWarp<Cf::LS>, N>(g, a, (int)(s / a.NF), (int)(s % a.NF), sm, h);
+        const bool ok = pd_stage_b_add<SubWarp<Cf::LS>, N, SPLIT>(g, a, (int)(s / a.NF), (int)(s % a.NF), sm, h);
         if (!ok && g.lane() == 0) {  // redone by k_stage_b
             sysflag[s] = 1;
             atomicAdd(nflagged, 1);
@@ -109,12 +141,12 @@ static int launch_tps(const PdStageB& a, const StageBPlan& p, double* hist, int3
     return (int)cudaGetLastError();
 }
 
-template <int N>
+template <int N, bool SPLIT>
 static void plan_add(StageBPlan& p, long nsys, int L) {
     using Cf = AddCfg<N>;
     int occ = 0;
-    if (cudaFuncSetAttribute(k_stage_b_add<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cf::SMEM) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stage_b_add<N>, Cf::THREADS, Cf::SMEM) != cudaSuccess || occ < 1) {
+    if (cudaFuncSetAttribute(k_stage_b_add<N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cf::SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stage_b_add<N, SPLIT>, Cf::THREADS, Cf::SMEM) != cudaSuccess || occ < 1) {
         cudaGetLastError();  // no device (sizing from a host-only process): plan for the compiled residency
         occ = Cf::MINB;
     }
@@ -124,14 +156,16 @@ static void plan_add(StageBPlan& p, long nsys, int L) {
     p.add_blocks = (int)blocks;
     p.add_slots = blocks * Cf::SPC;
     p.add_hist = (long)L * Cf::F::HIST_PER_LAYER;
+    p.split = SPLIT ? 1 : 0;
+    p.rt_doubles = SPLIT ? (size_t)nsys * L * N * (N + 1) : 0;
 }
 
-template <int N>
+template <int N, bool SPLIT>
 static int launch_add(const PdStageB& a, const StageBPlan& p, double* hist, int32_t* sysflag, cudaStream_t st) {
     using Cf = AddCfg<N>;
-    cudaError_t e = cudaFuncSetAttribute(k_stage_b_add<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cf::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_stage_b_add<N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cf::SMEM);
     if (e != cudaSuccess) return (int)e;
-    k_stage_b_add<N><<<p.add_blocks, Cf::THREADS, Cf::SMEM, st>>>(a, hist, p.add_hist, sysflag, sysflag + (p.flag_bytes - 256) / 4);
+    k_stage_b_add<N, SPLIT><<<p.add_blocks, Cf::THREADS, Cf::SMEM, st>>>(a, hist, p.add_hist, sysflag, sysflag + (p.flag_bytes - 256) / 4);
     return (int)cudaGetLastError();
 }
 
@@ -144,8 +178,8 @@ StageBPlan pd_plan_stage_b(int B, int NF, int N, int L, int flags) {
         switch (N) {
             case 2: plan_tps<2>(p, nsys, L); break;
             case 4: plan_tps<4>(p, nsys, L); break;
-            case 8: plan_add<8>(p, nsys, L); break;
-            default: plan_add<16>(p, nsys, L); break;
+            case 8: plan_add<8, true>(p, nsys, L); break;
+            default: plan_add<16, false>(p, nsys, L); break;
         }
         p.flag_bytes = (((size_t)nsys * sizeof(int32_t) + 255) & ~(size_t)255) + 256;  // + the counter of flagged systems
     }
@@ -185,18 +219,23 @@ int pd_launch_stage_b(const PdStageB& a, int flags, void* workspace, size_t work
     int32_t* sysflag = nullptr;
     if (pb.add) {
         sysflag = reinterpret_cast<int32_t*>(ws);
-        double* hist = reinterpret_cast<double*>(ws + pb.flag_bytes);
+        double* rt = reinterpret_cast<double*>(ws + pb.flag_bytes);
+        double* hist = rt + pb.rt_doubles;
         cudaError_t e = cudaMemsetAsync(sysflag, 0, pb.flag_bytes, st);
         if (e != cudaSuccess) return (int)e;
-        int rc;
+        PdStageB as = a;
+        as.RT = pb.split ? rt : nullptr;
+        int rc = 0;
+        if (pb.split) rc = launch_ops<8>(as, rt, st);
+        if (rc) return rc;
         switch (a.N) {
-            case 2: rc = launch_tps<2>(a, pb, hist, sysflag, st); break;
-            case 4: rc = launch_tps<4>(a, pb, hist, sysflag, st); break;
-            case 8: rc = launch_add<8>(a, pb, hist, sysflag, st); break;
-            default: rc = launch_add<16>(a, pb, hist, sysflag, st); break;
+            case 2: rc = launch_tps<2>(as, pb, hist, sysflag, st); break;
+            case 4: rc = launch_tps<4>(as, pb, hist, sysflag, st); break;
+            case 8: rc = launch_add<8, true>(as, pb, hist, sysflag, st); break;
+            default: rc = launch_add<16, false>(as, pb, hist, sysflag, st); break;
         }
         if (rc) return rc;
-        ws += pb.flag_bytes + (size_t)pb.add_slots * pb.add_hist * 8;
+        ws += pb.flag_bytes + (pb.rt_doubles + (size_t)pb.add_slots * pb.add_hist) * 8;
     }
     double* hist_b = reinterpret_cast<double*>(ws);
     switch (a.N) {

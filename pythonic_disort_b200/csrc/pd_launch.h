@@ -19,16 +19,19 @@ static inline int pd_lanes_for(int n) {
 }
 static inline cudaStream_t pd_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// Stage B launch plan and workspace layout: [system flags int32 | history of k_stage_b_add | history of k_stage_b]
+// Stage B launch plan and workspace layout (after the PD_WS_HEAD bytes):
+// [system flags int32 + counter | layer operators R^, T^ (N = 8) | history of the first kernel | history of k_stage_b]
 struct StageBPlan {
     int add;                 // 1: k_stage_b_add (2: k_stage_b_tps) runs first, k_stage_b only redoes the systems it flags
+    int split;               // 1: k_layer_ops forms R^, T^ of every layer first, the sweep only consumes them (N = 8)
+    size_t rt_doubles;       // B * NF * L * N (N + 1) if split
     int add_blocks;
     long add_slots, add_hist;  // resident systems and history doubles per system of that first kernel
     size_t flag_bytes;
     int wpb, sys_doubles, blocks;  // k_stage_b: warps per CTA, shared doubles per system, grid
     size_t smem;
     long hist_doubles, slots;
-    size_t bytes() const { return flag_bytes + ((size_t)add_slots * add_hist + (size_t)slots * hist_doubles) * 8; }
+    size_t bytes() const { return flag_bytes + (rt_doubles + (size_t)add_slots * add_hist + (size_t)slots * hist_doubles) * 8; }
 };
 StageBPlan pd_plan_stage_b(int B, int NF, int N, int L, int flags);
 int pd_check_cfg(const pd_config* c);

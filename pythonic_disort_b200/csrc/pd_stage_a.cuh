@@ -67,8 +67,7 @@ PD_HD void pd_stage_a_item(const Grp& g, const PdStageA& a, int b, int m, int l,
     const double omega = a.omega_s[(long)b * a.L + l];
     const double* wl = a.wleg + ((long)b * a.L + l) * a.NLeg + m;
     double* Kout = a.K + item * n;
-    double* Gp_out = a.G + item * 2 * n * n;
-    double* Gm_out = Gp_out + n * n;
+    double* Gout = a.G + pd_g_base(item, n);
     double* Bout = a.beam ? a.Bv + item * 2 * n : nullptr;
     const bool thermal = a.iso && m == 0;
     const bool beam = a.beam && a.colp[(long)b * PD_NCOLP + PD_COL_I0] > 0.0;  // per column (pydisort.py:215)
@@ -82,8 +81,8 @@ PD_HD void pd_stage_a_item(const Grp& g, const PdStageA& a, int b, int m, int l,
     if (!active) {  // :162-168
         for (int idx = lane; idx < n * n; idx += Grp::size) {
             const int i = idx / n, j = idx - i * n;
-            Gp_out[idx] = 0.0;
-            Gm_out[idx] = (i == j) ? 1.0 : 0.0;
+            Gout[pd_g_off(idx, n)] = 0.0;
+            Gout[pd_g_off(n * n + idx, n)] = (i == j) ? 1.0 : 0.0;
             if (thermal) {
                 A1[i * ld + j] = 0.0;
                 Z[i * ld + j] = (i == j) ? 1.0 : 0.0;
@@ -187,8 +186,8 @@ PD_HD void pd_stage_a_item(const Grp& g, const PdStageA& a, int b, int m, int l,
             const int i = idx / n, j = idx - i * n;
             const double v = Z[i * ld + j], u = H[i * ld + j];
             const double gp = 0.5 * (v + u) * dinv[i], gm = 0.5 * (v - u) * dinv[i];
-            Gp_out[idx] = gp;
-            Gm_out[idx] = gm;
+            Gout[pd_g_off(idx, n)] = gp;
+            Gout[pd_g_off(n * n + idx, n)] = gm;
             if (thermal) {
                 A1[i * ld + j] = gp;
                 Z[i * ld + j] = gm;

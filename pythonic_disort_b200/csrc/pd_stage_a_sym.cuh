@@ -64,16 +64,15 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
     for (int t = 0; t < nm; ++t) active |= (fabs((omega / 2) * wl[t]) > 1e-8);
     if (!active) {  // shortcut (:162-168): G = [[0, I], [I, 0]], K = 1/mu, B = 0
         double* Kout = a.K + item * N;
-        double* Gp_out = a.G + item * 2 * N * N;
-        double* Gm_out = Gp_out + N * N;
+        double* Gout = a.G + pd_g_base(item, N);
         double* Bout = a.beam ? a.Bv + item * 2 * N : nullptr;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             Kout[i] = 1.0 / a.mu[i];
 #pragma unroll
             for (int j = 0; j < N; ++j) {
-                Gp_out[i * N + j] = 0.0;
-                Gm_out[i * N + j] = (i == j) ? 1.0 : 0.0;
+                Gout[pd_g_off(i * N + j, N)] = 0.0;
+                Gout[pd_g_off(N * N + i * N + j, N)] = (i == j) ? 1.0 : 0.0;
             }
             if (a.beam) {
                 Bout[i] = 0.0;
@@ -292,8 +291,7 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
     // ---- K, G blocks:  V^ = L^-T W,  U^ = -L W / k;  Gp = (V^ + U^)/(2 D),  Gm = (V^ - U^)/(2 D) ----
     // (output pointers are formed only now: nothing but `item` has to stay live across the Jacobi sweeps)
     double* Kout = a.K + item * N;
-    double* Gp_out = a.G + item * 2 * N * N;
-    double* Gm_out = Gp_out + N * N;
+    double* Gout = a.G + pd_g_base(item, N);
     double* Bout = a.beam ? a.Bv + item * 2 * N : nullptr;
     double dinv[N];
 #pragma unroll
@@ -341,8 +339,8 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
         }
 #pragma unroll
         for (int j = 0; j < N; j += 4) {
-            pd_store4(Gp_out + r * N + j, gp[j], gp[j + 1], gp[j + 2], gp[j + 3]);
-            pd_store4(Gm_out + r * N + j, gm[j], gm[j + 1], gm[j + 2], gm[j + 3]);
+            pd_store4(Gout + pd_g_off(r * N + j, N), gp[j], gp[j + 1], gp[j + 2], gp[j + 3]);
+            pd_store4(Gout + pd_g_off(N * N + r * N + j, N), gm[j], gm[j + 1], gm[j + 2], gm[j + 3]);
         }
     }
 

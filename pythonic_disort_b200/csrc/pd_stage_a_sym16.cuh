@@ -411,8 +411,7 @@ __device__ __forceinline__ bool pd_stage_a_j16_item(const PdStageA& a, int b, in
 
     // ---- K and the G blocks: Gp = (V^ + U^) / (2 D), Gm = (V^ - U^) / (2 D); shortcut layers (:162-168) ----
     double* Kout = a.K + item * 16;
-    double* Gp_out = a.G + item * 512;
-    double* Gm_out = Gp_out + 256;
+    double* Gout = a.G + pd_g_base(item, 16);
     if (store) {
         if (active) {
             pd_st2(Kout + 2 * lam, ka, kb);
@@ -431,8 +430,8 @@ __device__ __forceinline__ bool pd_stage_a_j16_item(const PdStageA& a, int b, in
                 gma = (i == 2 * lam) ? 1.0 : 0.0;
                 gmb = (i == 2 * lam + 1) ? 1.0 : 0.0;
             }
-            pd_st2(Gp_out + i * 16 + 2 * lam, gpa, gpb);
-            pd_st2(Gm_out + i * 16 + 2 * lam, gma, gmb);
+            pd_st2(Gout + pd_g_off(i * 16 + 2 * lam, 16), gpa, gpb);
+            pd_st2(Gout + pd_g_off(256 + i * 16 + 2 * lam, 16), gma, gmb);
         }
     }
 

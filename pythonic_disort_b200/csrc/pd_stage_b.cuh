@@ -27,7 +27,9 @@ struct PdStageB {
     const double* bdrf_q;  // [(B)][NBDRF][N][N]
     const double* bdrf_q0; // [(B)][NBDRF][N]
     const double* K;       // [B][NF][L][N]
-    const double* G;       // [B][NF][L][2][N][N]
+    const double* G;       // [B][NF][L][2][N][N] (N = 8: sector-interleaved over 32 items, pd_common.cuh)
+    const double* RT;      // [B][NF][L][2][N(N+1)/2] layer operators R^, T^, packed symmetric (k_layer_ops, N = 8), or
+                           // null: the sweep forms them from G
     const double* Bv;      // [B][NF][L][2N]
     const double* dth;     // [B][L][Ns][2N]
     double* C;             // [B][NF][L][2N]
@@ -61,7 +63,7 @@ PD_HD void pd_stage_b_system(const Grp& g, const PdStageB& a, int b, int m, doub
     const long sys = (long)b * a.NF + m;
     const double* taus = a.taus + (long)b * (L + 1);
     const double* Kc = a.K + sys * L * n;
-    const double* Gc = a.G + sys * L * 2 * n * n;
+    const long item0 = sys * L;  // G item of layer l: item0 + l (pd_g_base / pd_g_off, pd_common.cuh)
     const double* Bc = a.beam ? a.Bv + sys * L * n2 : nullptr;  // only read when `beam`
     const double* dthc = (a.iso && m == 0) ? a.dth + (long)b * L * a.Ns * n2 : nullptr;
     const double mu0 = a.colp[(long)b * PD_NCOLP + PD_COL_MU0];
@@ -76,7 +78,7 @@ PD_HD void pd_stage_b_system(const Grp& g, const PdStageB& a, int b, int m, doub
     // G_l[r][c] for r, c in [0, 2n): block structure [[Gp, Gm], [Gm, Gp]]
     auto Gat = [&](int l, int r, int c) -> double {
         const int rb = r >= n, cb = c >= n;
-        return Gc[((long)l * 2 + (rb ^ cb)) * n * n + (r - rb * n) * n + (c - cb * n)];
+        return a.G[pd_g_base(item0 + l, n) + pd_g_off((rb ^ cb) * n * n + (r - rb * n) * n + (c - cb * n), n)];
     };
 
     if (has_bdrf) {  // R = (1 + delta_m0) q^m(mu_i, mu_j) mu_j w_j   (:121-134)

@@ -115,7 +115,9 @@ PD_HD double pd_add_gj_solve(const Grp& g, int lane, double (&Mc)[N / Grp::size]
     return minpiv;
 }
 
-template <class Grp, int N>
+// SPLIT: the layer operators R^, T^ come precomputed (A.RT, packed symmetric, pd_layer_ops.cuh) instead of being
+// formed in the sweep.
+template <class Grp, int N, bool SPLIT = false>
 PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double* sm, double* hist) {
     using F = PdStageBAdd<N, Grp::size>;
     constexpr int LS = Grp::size, NJ = N / LS, N2 = 2 * N, NN = N * N, LD = F::LDM, MAT = F::MAT;
@@ -134,7 +136,9 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
     const long sys = (long)b * A.NF + m;
     const double* taus = A.taus + (long)b * (L + 1);
     const double* Kc = A.K + sys * L * N;
-    const double* Gc = A.G + sys * L * 2 * NN;
+    const long item0 = sys * L;  // G item of layer l: item0 + l (layout: pd_common.cuh)
+    constexpr int NP = N * (N + 1) / 2;
+    const double* RTc = SPLIT ? A.RT + item0 * 2 * NP : nullptr;
     const double* Bc = A.beam ? A.Bv + sys * L * N2 : nullptr;
     const double* dthc = (A.iso && m == 0) ? A.dth + (long)b * L * A.Ns * N2 : nullptr;
     const double mu0 = A.colp[(long)b * PD_NCOLP + PD_COL_MU0];
@@ -147,27 +151,38 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
     const double rmu0 = beam ? 1.0 / mu0 : 0.0;
     bool bad = false;
 
-    // layer ll (G blocks, k, beam vector) -> the staging block (asynchronously on the GPU)
-    auto stage = [&](int ll) {
+    // layer ll (G blocks or packed R^, T^; k; beam vector) -> the staging block (asynchronously on the GPU)
+    auto stage_any = [&](int ll, bool ops) {
         double* dst = ring;
-        const double* gs = Gc + (long)ll * 2 * NN;
         const double* ks = Kc + (long)ll * N;
+        const double* gs = A.G + pd_g_base(item0 + ll, N);
 #if defined(__CUDA_ARCH__)
-        for (int ch = lane; ch < NN; ch += LS) {  // 16-byte chunk ch = (row ch / (N/2), column pair ch % (N/2)) of [2N][N]
-            const int r = ch / (N / 2), c2 = 2 * (ch % (N / 2));
-            pd_cp_async16(dst + r * LD + (c2 ^ F::sw(r)), gs + 2 * ch);
+        if (ops) {
+            const double* rs = RTc + (long)ll * 2 * NP;
+            for (int ch = lane; ch < NP; ch += LS) pd_cp_async16(dst + 2 * ch, rs + 2 * ch);
+        } else {
+            for (int ch = lane; ch < NN; ch += LS) {  // 16-byte chunk ch = (row ch / (N/2), column pair ch % (N/2)) of [2N][N]
+                const int r = ch / (N / 2), c2 = 2 * (ch % (N / 2));
+                pd_cp_async16(dst + r * LD + (c2 ^ F::sw(r)), gs + pd_g_off(2 * ch, N));
+            }
         }
         for (int ch = lane; ch < N / 2; ch += LS) pd_cp_async16(dst + 2 * MAT + 2 * ch, ks + 2 * ch);
         if (Bc)
             for (int ch = lane; ch < N; ch += LS) pd_cp_async16(dst + 2 * MAT + N + 2 * ch, Bc + (long)ll * N2 + 2 * ch);
 #else
-        for (int i = 0; i < 2 * N; ++i)
-            for (int k = 0; k < N; ++k) dst[i * LD + (k ^ F::sw(i))] = gs[i * N + k];
+        if (ops) {
+            for (int i = 0; i < 2 * NP; ++i) dst[i] = RTc[(long)ll * 2 * NP + i];
+        } else {
+            for (int i = 0; i < 2 * N; ++i)
+                for (int k = 0; k < N; ++k) dst[i * LD + (k ^ F::sw(i))] = gs[pd_g_off(i * N + k, N)];
+        }
         for (int i = 0; i < N; ++i) dst[2 * MAT + i] = ks[i];
         if (Bc)
             for (int i = 0; i < N2; ++i) dst[2 * MAT + N + i] = Bc[(long)ll * N2 + i];
 #endif
     };
+    auto stage = [&](int ll) { stage_any(ll, false); };          // eigenvectors (back sweep; forward sweep if !SPLIT)
+    auto stage_fwd = [&](int ll) { stage_any(ll, SPLIT); };      // what the forward sweep consumes
     auto stage_wait = [&]() {
 #if defined(__CUDA_ARCH__)
         pd_cp_async_wait_all();
@@ -260,7 +275,17 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
         }
         S[jj] = Dj[jj] * (have_b ? bneg[j] : 0.0);
     }
-    stage(0);
+    int rt_off[SPLIT ? NJ : 1][SPLIT ? N : 1];  // packed index of (i, j) for the columns j this lane owns
+    if (SPLIT) {
+#pragma unroll
+        PD_FOR_OWN(jj, j)
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int lo = i < j ? i : j, hi = i < j ? j : i;
+                rt_off[SPLIT ? jj : 0][SPLIT ? i : 0] = lo * N - lo * (lo - 1) / 2 + (hi - lo);
+            }
+    }
+    stage_fwd(0);
     double att_t = 1.0;  // exp(-tau*_l / mu0), tau*_0 = 0
     for (int l = 0; l < L; ++l) {
         stage_wait();
@@ -271,7 +296,33 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
         const double att_b = beam ? exp(-taus[l + 1] * rmu0) : 0.0;
 
         double Rh[NJ][N], Th[NJ][N], blp[NJ], blm[NJ];
-        {
+        if (SPLIT) {
+            // columns j of the symmetric R^, T^ out of their packed copies; column-major copies for the other lanes
+#pragma unroll
+            PD_FOR_OWN(jj, j) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const int o = rt_off[SPLIT ? jj : 0][SPLIT ? i : 0];
+                    Rh[jj][i] = Gl[o];
+                    Th[jj][i] = Gl[NP + o];
+                }
+                blp[jj] = beam ? Bl[j] : 0.0;
+                blm[jj] = beam ? Bl[N + j] : 0.0;
+            }
+            bad = bad || !(Gl[0] == Gl[0]);  // NaN mark of pd_layer_ops_item
+            g.sync();  // every lane has unpacked the staged layer: refill it behind the arithmetic
+            if (l + 1 < L) stage_fwd(l + 1);
+#pragma unroll
+            PD_FOR_OWN(jj, j) {
+#pragma unroll
+                for (int i = 0; i < N; i += 2) {
+                    pd_d2 r2, t2;
+                    r2.x = Rh[jj][i]; r2.y = Rh[jj][i + 1]; t2.x = Th[jj][i]; t2.y = Th[jj][i + 1];
+                    *reinterpret_cast<pd_d2*>(Rc + j * LD + (i ^ F::sw(j))) = r2;
+                    *reinterpret_cast<pd_d2*>(Tc + j * LD + (i ^ F::sw(j))) = t2;
+                }
+            }
+        } else {
             double vrow[NJ][N], urow[NJ][N];
             eigvec_columns(Gl, vrow, urow);
             // d_k = -tanh(k dtau / 2) / g_k by the lane that owns k
@@ -294,7 +345,7 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
                 blm[kk] = beam ? Bl[N + k] : 0.0;
             }
             g.sync();
-            if (l + 1 < L) stage(l + 1);  // the staged copy of layer l is used up: fetch the next one behind the arithmetic
+            if (l + 1 < L) stage_fwd(l + 1);  // the staged copy of layer l is used up: fetch the next one behind the arithmetic
             // columns j of I + U^ d U^T and I + V^ d V^T
             double X1[NJ][N], X2[NJ][N];
 #pragma unroll
@@ -435,6 +486,7 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
         att_t = att_b;
     }
     g.sync();
+    if (SPLIT) stage(L - 1);  // the back sweep starts from the eigenvectors of the last layer
 
     // ---------------------------------------------------------------- surface  (_solve_for_coeffs.py:121-134, :163, :248-254)
     double ubp[NJ], ubm[NJ];  // u^+ and u^- at the bottom interface of the current layer
@@ -508,7 +560,7 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
         }
     };
     load_history(L - 1);
-    double att_b = att_t;  // exp(-tau*_L / mu0); the staging block still holds layer L - 1
+    double att_b = att_t;  // exp(-tau*_L / mu0); the staging block holds (SPLIT: is being refilled with) layer L - 1
     for (int l = L - 1; l >= 0; --l) {
         const double dtau = taus[l + 1] - taus[l];
         const double at = beam ? exp(-taus[l] * rmu0) : 0.0;

@@ -44,7 +44,7 @@ PD_HD bool pd_stage_b_tps(const PdStageB& A, int b, int m, double* hist, long hs
     const long sys = (long)b * A.NF + m;
     const double* taus = A.taus + (long)b * (L + 1);
     const double* Kc = A.K + sys * L * N;
-    const double* Gc = A.G + sys * L * 2 * NN;
+    const long item0 = sys * L;  // G item of layer l: item0 + l, sector-interleaved over 32 items (pd_common.cuh)
     const double* Bc = A.beam ? A.Bv + sys * L * N2 : nullptr;
     const double* dthc = (A.iso && m == 0) ? A.dth + (long)b * L * A.Ns * N2 : nullptr;
     const double mu0 = A.colp[(long)b * PD_NCOLP + PD_COL_MU0];
@@ -63,14 +63,14 @@ PD_HD bool pd_stage_b_tps(const PdStageB& A, int b, int m, double* hist, long hs
 
     // V^ = D (Gp + Gm) / 2, U^ = D (Gp - Gm) / 2 of layer l
     auto eigvecs = [&](int l, double (&V)[N][N], double (&U)[N][N]) {
-        const double* Gl = Gc + (long)l * 2 * NN;
+        const double* Gl = A.G + pd_g_base(item0 + l, N);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const double h = 0.5 * D[i];
 #pragma unroll
             for (int k = 0; k < N; k += 2) {
-                const pd_d2 gp = *reinterpret_cast<const pd_d2*>(Gl + i * N + k);
-                const pd_d2 gm = *reinterpret_cast<const pd_d2*>(Gl + NN + i * N + k);
+                const pd_d2 gp = *reinterpret_cast<const pd_d2*>(Gl + pd_g_off(i * N + k, N));
+                const pd_d2 gm = *reinterpret_cast<const pd_d2*>(Gl + pd_g_off(NN + i * N + k, N));
                 V[i][k] = h * (gp.x + gm.x);
                 V[i][k + 1] = h * (gp.y + gm.y);
                 U[i][k] = h * (gp.x - gm.x);
@@ -128,9 +128,9 @@ PD_HD bool pd_stage_b_tps(const PdStageB& A, int b, int m, double* hist, long hs
     // reader of its 2 N^2 + 5 N + ... doubles per layer, so nothing else hides that latency)
     auto prefetch_layer = [&](int l) {
 #if defined(__CUDA_ARCH__)
-        const char* gp = reinterpret_cast<const char*>(Gc + (long)l * 2 * NN);
+        const double* gp = A.G + pd_g_base(item0 + l, N);
 #pragma unroll
-        for (int o = 0; o < 2 * NN * 8; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(gp + o));
+        for (int e = 0; e < 2 * NN; e += 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(gp + pd_g_off(e, N)));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(Kc + (long)l * N));
         if (Bc) asm volatile("prefetch.global.L1 [%0];" ::"l"(Bc + (long)l * N2));
         if (dthc) asm volatile("prefetch.global.L1 [%0];" ::"l"(dthc + (long)l * A.Ns * N2));

@@ -15,15 +15,35 @@
 #include "../../pythonic_disort_b200/csrc/pd_stage_a.cuh"
 #include "../../pythonic_disort_b200/csrc/pd_stage_a_sym.cuh"
 #include "../../pythonic_disort_b200/csrc/pd_stage_b.cuh"
+#include "../../pythonic_disort_b200/csrc/pd_layer_ops.cuh"
 #include "../../pythonic_disort_b200/csrc/pd_stage_b_add.cuh"
 #include "../../pythonic_disort_b200/csrc/pd_stage_b_tps.cuh"
 
+// same dispatch as pd_launch_stage_b: for N = 8 the layer operators R^, T^ are formed first, one item at a time
+// (pd_layer_ops.cuh), and the sweep runs in its SPLIT form
 template <int N>
-static bool host_stage_b_add(const PdStageB& sb, int b, int m, double* hist) {
+static bool host_stage_b_add(const PdStageB& sb_in, int b, int m, double* hist) {
     SerialGroup g;
+    PdStageB sb = sb_in;
+    constexpr bool SPLIT = (N == 8);
     double* sm = (double*)malloc(sizeof(double) * PdStageBAdd<N>::SD);
-    const bool ok = pd_stage_b_add<SerialGroup, N>(g, sb, b, m, sm, hist);
+    double* rt = nullptr;
+    if (SPLIT) {
+        const long sys = (long)b * sb.NF + m;
+        constexpr int NP2 = N * (N + 1);
+        rt = (double*)malloc(sizeof(double) * sb.L * NP2);
+        double hD[N], park[N * (N + 1) / 2];
+        for (int i = 0; i < N; ++i) hD[i] = 0.5 * sqrt(sb.w[i] * sb.mu[i]);
+        for (int l = 0; l < sb.L; ++l) {
+            const double* ts = sb.taus + (long)b * (sb.L + 1) + l;
+            pd_layer_ops_item<N>(sb.G + pd_g_base(sys * sb.L + l, N), sb.K + (sys * sb.L + l) * N, ts[1] - ts[0], hD,
+                                 rt + (long)l * NP2, park, 1);
+        }
+        sb.RT = rt - sys * sb.L * NP2;  // the sweep indexes RT by item
+    }
+    const bool ok = pd_stage_b_add<SerialGroup, N, SPLIT>(g, sb, b, m, sm, hist);
     free(sm);
+    free(rt);
     return ok;
 }
 
@@ -112,7 +132,7 @@ int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const 
     sb.B = cfg->B; sb.L = cfg->L; sb.N = N; sb.NF = cfg->NFourier; sb.Ns = cfg->Nscoeffs; sb.NBDRF = cfg->NBDRF;
     sb.NFb = cfg->NFb; sb.beam = a.beam; sb.iso = a.iso; sb.bdrf_percol = (cfg->flags & PD_FLAG_BDRF_PERCOL) != 0;
     sb.taus = taus; sb.colp = colp; sb.bpos = bpos_s; sb.bneg = bneg_s; sb.mu = mu_nodes; sb.w = w_nodes;
-    sb.bdrf_q = bdrf_q; sb.bdrf_q0 = bdrf_q0; sb.K = K; sb.G = G; sb.Bv = Bv; sb.dth = dth; sb.C = C;
+    sb.bdrf_q = bdrf_q; sb.bdrf_q0 = bdrf_q0; sb.K = K; sb.G = G; sb.RT = nullptr; sb.Bv = Bv; sb.dth = dth; sb.C = C;
     sb.status = status;
     double* smb = (double*)malloc(sizeof(double) * (pd_stage_b_doubles(N) + 16));
     // same dispatch as pd_launch_stage_b: interface-radiance elimination for N = 2, 4 (thread per system), 8, 16 (unless
