@@ -187,7 +187,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # kernels launched per C-ABI call (label of the event mark api.py records around it)
 def _launches(label, N, nt):
-    return {"prologue": 1, "solve_eigen": 2 if N in (4, 8, 16) else 1, "solve_bc": 2 if N in (2, 4, 8, 16) else 1,
+    return {"prologue": 1, "solve_eigen": 2 if N in (4, 8, 16) else 1, "solve_bc": 3 if N == 8 else 2 if N in (2, 4, 16) else 1,
             "eval_flux": 1, "eval_u0": 1, "eval_u": 2 if nt else 1, "interp_mu": 1}.get(label, 1)
 
 
@@ -376,8 +376,10 @@ class Bench:
         bytes_k = {"solve_eigen": item * (NQuad + 1) * 8 + item * (2 * N * N + N + 2 * N) * 8,
                    "solve_bc": item * (2 * N * N + N + 2 * N) * 8 + item * 2 * N * 8}[dom]
         kname = {"solve_eigen": "k_stage_a_sym" if N in (4, 8) else "k_stage_a_j16" if N == 16 else "k_stage_a",
-                 "solve_bc": "k_stage_b_tps" if N in (2, 4) else "k_stage_b_add" if N in (8, 16) else "k_stage_b"}[dom]
-        per_col = self.traffic.get(workload, {}).get(kname)
+                 "solve_bc": "k_stage_b_tps" if N in (2, 4) else "k_layer_ops + k_stage_b_add" if N == 8 else
+                 "k_stage_b_add" if N == 16 else "k_stage_b"}[dom]   # the kernels the stage's event time covers
+        parts = [self.traffic.get(workload, {}).get(k.strip()) for k in kname.split("+")]
+        per_col = sum(parts) if all(parts) else None
         peak = self.fp64_peak
         roofline = {"kernel": kname, "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak if peak > 0 else None,

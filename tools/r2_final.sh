@@ -7,7 +7,7 @@ timeout 2400 python -m pytest tests -m gpu -q --durations=5 2>&1 | tail -12 > gp
 timeout 1200 python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2>/dev/null
 for w in "sw 2048" "lw 32768" "ha 256"; do set -- $w
-ncu --set full --clock-control none -k regex:"^k_(prologue|stage|eval|nt|interp)" -c 12 \
+ncu --set full --clock-control none -k regex:"^k_(prologue|stage|layer|eval|nt|interp)" -c 12 \
     -o /tmp/prof_$1 python bench.py --workload $1 --steps 1 --warmup 0 --columns $2 --chunk $2 --no-cpu --no-others > gpurun_out/r2_ncu_$1.log 2>&1
 ncu -i /tmp/prof_$1.ncu-rep --page raw --csv > gpurun_out/r2_raw_$1.csv
 done
