@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PD_ABI_VERSION 1
+#define PD_ABI_VERSION 2
 #define PD_MAX_NQUAD 92   /* largest NQuad: one system's elimination panel (size-generic stage B) must fit one CTA's
                            * 227 KB of shared memory; larger values are rejected by every entry point (-8)        */
 
@@ -126,6 +126,11 @@ int pd_prologue(const pd_config* cfg,
  *      Bv [B][NFourier][L][2N]     beam particular solution (B_collect)
  *      dth[B][L][Ns][2N]           thermal particular solution, coefficient of tau*^q
  *      C  [B][NFourier][L][2N]     boundary-condition coefficients (GC_collect = G * C)
+ *      Uif[B][L+1][NFourier][2N]   radiances u^m of the 2N streams at the L + 1 layer interfaces (0 = top), particular
+ *                                   solutions included, not multiplied by rescale_factor: what the continuity rows of
+ *                                   _solve_for_coeffs.py:184-205 equate on the two sides of an interface.  The
+ *                                   evaluation entry points return these for query points that ARE interfaces instead
+ *                                   of re-assembling G (C * exp) there (pd_state.Uif).  May be NULL (not written).
  *      status[B] int32             PD_ST_* bits */
 int pd_solve(const pd_config* cfg,
              const double* taus, const double* omega_s, const double* wleg, const double* s_s,
@@ -133,13 +138,13 @@ int pd_solve(const pd_config* cfg,
              const double* mu_nodes, const double* w_nodes, const double* ptab,
              const double* bdrf_q, const double* bdrf_q0,
              void* workspace, size_t workspace_bytes,
-             double* K, double* G, double* Bv, double* dth, double* C, int32_t* status,
+             double* K, double* G, double* Bv, double* dth, double* C, double* Uif, int32_t* status,
              void* stream);
 
 /* Same as pd_solve but runs only the stages selected in `stages`
  * (PD_STAGE_EIGEN: per-(column, mode, layer) eigen-decomposition and particular
  * solutions -> K, G, Bv, dth;  PD_STAGE_BC: per-(column, mode) boundary-condition
- * solve -> C).  Lets callers time or re-run the two kernels separately. */
+ * solve -> C, Uif).  Lets callers time or re-run the two kernels separately. */
 #define PD_STAGE_EIGEN 1
 #define PD_STAGE_BC    2
 int pd_solve_stages(const pd_config* cfg, int stages,
@@ -148,12 +153,14 @@ int pd_solve_stages(const pd_config* cfg, int stages,
              const double* mu_nodes, const double* w_nodes, const double* ptab,
              const double* bdrf_q, const double* bdrf_q0,
              void* workspace, size_t workspace_bytes,
-             double* K, double* G, double* Bv, double* dth, double* C, int32_t* status,
+             double* K, double* G, double* Bv, double* dth, double* C, double* Uif, int32_t* status,
              void* stream);
 
 /* Output functions evaluated at ntau optical depths per column
  * (tau_q[B][ntau], unscaled tau as the user gives it; each value must lie in
  * [0, tau_L], checked by the caller).  `anti` != 0 selects the tau-antiderivative.
+ * A query point equal to 0 or to one of the column's tau[l] (bit for bit) is a layer interface: with st->Uif set and
+ * anti == 0 its mode radiances are read from Uif (the same quantity to rounding; G is not read for that point).
  *
  * pd_eval_flux : flux_up / flux_down, _assemble_intensity_and_fluxes.py:446-613
  *   out Fup[B][ntau] Fdn_diffuse[B][ntau] Fdn_direct[B][ntau]
@@ -176,6 +183,7 @@ typedef struct pd_state {
     const double* C;
     const double* mu_nodes;
     const double* w_nodes;
+    const double* Uif;       /* [B][L+1][NFourier][2N] from pd_solve, or NULL: every point is assembled from G, C   */
 } pd_state;
 
 int pd_eval_flux(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau, int anti,

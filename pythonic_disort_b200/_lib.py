@@ -27,7 +27,7 @@ class pd_config(ctypes.Structure):
 
 class pd_state(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
-                ("tau", "taus", "scale_tau", "colp", "K", "G", "Bv", "dth", "C", "mu_nodes", "w_nodes")]
+                ("tau", "taus", "scale_tau", "colp", "K", "G", "Bv", "dth", "C", "mu_nodes", "w_nodes", "Uif")]
 
 
 # constants of include/pydisort_b200.h
@@ -88,9 +88,9 @@ def bind(path):
     lib.pd_prologue.restype = ci
     lib.pd_prologue.argtypes = [cfgp] + [vp] * 11 + [ci] + [vp] * 10 + [vp]
     lib.pd_solve.restype = ci
-    lib.pd_solve.argtypes = [cfgp] + [vp] * 13 + [vp, ctypes.c_size_t] + [vp] * 6 + [vp]
+    lib.pd_solve.argtypes = [cfgp] + [vp] * 13 + [vp, ctypes.c_size_t] + [vp] * 7 + [vp]
     lib.pd_solve_stages.restype = ci
-    lib.pd_solve_stages.argtypes = [cfgp, ci] + [vp] * 13 + [vp, ctypes.c_size_t] + [vp] * 6 + [vp]
+    lib.pd_solve_stages.argtypes = [cfgp, ci] + [vp] * 13 + [vp, ctypes.c_size_t] + [vp] * 7 + [vp]
     lib.pd_eval_flux.restype = ci
     lib.pd_eval_flux.argtypes = [cfgp, stp, vp, ci, ci, vp, vp, vp, vp]
     lib.pd_eval_u0.restype = ci
@@ -107,7 +107,7 @@ def bind(path):
     lib.pd_hapke_modes.argtypes = [ci, ctypes.c_long, ci, ci, vp, vp, vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, vp, vp]
     lib.pd_fp64_probe.restype = ctypes.c_double
     lib.pd_fp64_probe.argtypes = [vp, ci, vp]
-    if lib.pd_abi_version() != 1:
+    if lib.pd_abi_version() != 2:
         raise RuntimeError("libpydisort_b200 ABI mismatch")
     return lib
 

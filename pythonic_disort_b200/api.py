@@ -175,7 +175,7 @@ class _Solution:
         st = _lib.pd_state()
         for name, t in (("tau", self.tau), ("taus", self.taus), ("scale_tau", self.scale_tau), ("colp", self.colp),
                         ("K", self.K), ("G", self.G), ("Bv", self.Bv), ("dth", self.dth), ("C", self.C),
-                        ("mu_nodes", self.mu_d), ("w_nodes", self.w_d)):
+                        ("mu_nodes", self.mu_d), ("w_nodes", self.w_d), ("Uif", getattr(self, "Uif", None))):
             setattr(st, name, t.data_ptr() if t is not None else None)
         return st
 
@@ -694,13 +694,15 @@ def pydisort(
     sol.Bv = new(B, NFourier, L, NQuad) if beam else None
     sol.dth = new(B, L, Ns, NQuad) if Ns > 0 else None
     sol.C = new(B, NFourier, L, NQuad)
+    # stream radiances of every mode at the L + 1 interfaces: what the output functions return at levels that are interfaces
+    sol.Uif = new(B, L + 1, NFourier, NQuad)
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     ws_bytes = lib.pd_workspace_bytes(ctypes.byref(cfg))
     workspace = torch.empty(max(ws_bytes // 8, 1), dtype=_F64, device=dev)
     solve_args = (_ptr(sol.taus), _ptr(sol.omega_s), _ptr(sol.wleg), _ptr(sol.s_s), _ptr(sol.colp), _ptr(bpos_s),
                   _ptr(bneg_s), _ptr(pmu0), _ptr(mu_d), _ptr(w_d), _ptr(ptab), _ptr(bdrf_q), _ptr(bdrf_q0),
                   _ptr(workspace), ws_bytes, _ptr(sol.K), _ptr(sol.G), _ptr(sol.Bv), _ptr(sol.dth), _ptr(sol.C),
-                  _ptr(status), stream)
+                  _ptr(sol.Uif), _ptr(status), stream)
     _mark("begin", dev)
     sol._check(lib.pd_solve_stages(ctypes.byref(cfg), 1, *solve_args), "pd_solve (eigen stage)")
     _mark("solve_eigen", dev)

@@ -68,7 +68,7 @@ int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const 
                     const double* s_s, const double* colp, const double* bpos_s, const double* bneg_s,
                     const double* pmu0, const double* mu_nodes, const double* w_nodes, const double* ptab,
                     const double* bdrf_q, const double* bdrf_q0, void* workspace, size_t workspace_bytes, double* K,
-                    double* G, double* Bv, double* dth, double* C, int32_t* status, void* stream) {
+                    double* G, double* Bv, double* dth, double* C, double* Uif, int32_t* status, void* stream) {
     if (int e = pd_check_cfg(cfg)) return e;
     const int N = cfg->NQuad / 2;
     const bool beam = (cfg->flags & PD_FLAG_BEAM) != 0, iso = (cfg->flags & PD_FLAG_ISO) != 0;
@@ -89,7 +89,7 @@ int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const 
         sb.NFb = cfg->NFb; sb.beam = beam; sb.iso = iso; sb.bdrf_percol = (cfg->flags & PD_FLAG_BDRF_PERCOL) != 0;
         sb.taus = taus; sb.colp = colp; sb.bpos = bpos_s; sb.bneg = bneg_s; sb.mu = mu_nodes; sb.w = w_nodes;
         sb.bdrf_q = bdrf_q; sb.bdrf_q0 = bdrf_q0; sb.K = K; sb.G = G; sb.RT = nullptr; sb.Bv = Bv; sb.dth = dth; sb.C = C;
-        sb.status = status;
+        sb.Uif = Uif; sb.status = status;
         if (!workspace || workspace_bytes < PD_WS_HEAD) return -20;
         if (int rc = pd_launch_stage_b(sb, cfg->flags, static_cast<char*>(workspace) + PD_WS_HEAD, workspace_bytes - PD_WS_HEAD,
                                        pd_stream(stream)))
@@ -102,10 +102,10 @@ int pd_solve(const pd_config* cfg, const double* taus, const double* omega_s, co
              const double* colp, const double* bpos_s, const double* bneg_s, const double* pmu0,
              const double* mu_nodes, const double* w_nodes, const double* ptab, const double* bdrf_q,
              const double* bdrf_q0, void* workspace, size_t workspace_bytes, double* K, double* G, double* Bv,
-             double* dth, double* C, int32_t* status, void* stream) {
+             double* dth, double* C, double* Uif, int32_t* status, void* stream) {
     return pd_solve_stages(cfg, PD_STAGE_EIGEN | PD_STAGE_BC, taus, omega_s, wleg, s_s, colp, bpos_s, bneg_s, pmu0,
                            mu_nodes, w_nodes, ptab, bdrf_q, bdrf_q0, workspace, workspace_bytes, K, G, Bv, dth, C,
-                           status, stream);
+                           Uif, status, stream);
 }
 
 double pd_fp64_probe(double* sink, int iters, void* stream) {

@@ -48,6 +48,24 @@ PD_HD double pd_scaled_tau(const PdEval& a, int b, int l, double t) {
     return taus[l + 1] - (tau[l] - t) * a.st.scale_tau[(long)b * a.L + l];
 }
 
+// Interface hit: a query point that IS a layer interface (0, or bit for bit one of the column's tau[l]) takes the
+// radiances the boundary-condition sweep stored for that interface (pd_state.Uif; pd_stage_b*.cuh) instead of
+// G_l (C_l * e) + particular -- the same quantity to rounding, without reading G.  Returns the interface index or -1.
+PD_HD int pd_interface_level(const PdEval& a, int b, int l, double tq) {
+    if (!a.st.Uif || a.anti) return -1;
+    if (tq == a.st.tau[(long)b * a.L + l]) return l + 1;  // bottom of the point's layer (pd_locate: first l with tq <= tau[l])
+    return (tq == 0.0) ? 0 : -1;
+}
+
+// u^m of interface `lev` into uv[2n] (shared)
+template <class Grp>
+PD_HD void pd_mode_at_interface(const Grp& g, const PdEval& a, int b, int m, int lev, double* uv) {
+    const int n2 = 2 * a.N;
+    const double* us = a.st.Uif + pd_uif_index(b, lev, m, a.L, a.NF, n2);
+    for (int i = g.lane(); i < n2; i += Grp::size) uv[i] = us[i];
+    g.sync();
+}
+
 // u^m at one point into uv[2n] (shared); ev[2n] is scratch.  Includes the beam
 // and (m = 0) thermal particular solutions; NOT multiplied by rescale_factor.
 // beam attenuation factor of a query point: exp(-tau* / mu0) (its tau-antiderivative if a.anti), 0 without a beam
@@ -144,7 +162,9 @@ PD_HD void pd_flux_point(const Grp& g, const PdEval& a, int b, int t, double* sm
     const double ts = pd_scaled_tau(a, b, l, tq);
     double* ev = sm;
     double* uv = sm + 2 * n;
-    pd_mode_at<Grp, NC>(g, a, b, 0, l, ts, pd_beam_factor(a, b, l, ts), ev, uv);
+    const int lev = pd_interface_level(a, b, l, tq);
+    if (lev >= 0) pd_mode_at_interface(g, a, b, 0, lev, uv);
+    else pd_mode_at<Grp, NC>(g, a, b, 0, l, ts, pd_beam_factor(a, b, l, ts), ev, uv);
     if (g.lane() == 0) {
         double up = 0.0, dn = 0.0;
         for (int i = 0; i < n; ++i) {
@@ -183,7 +203,9 @@ PD_HD void pd_u0_point(const Grp& g, const PdEval& a, int b, int t, double* sm, 
     const double ts = pd_scaled_tau(a, b, l, tq);
     double* ev = sm;
     double* uv = sm + n2;
-    pd_mode_at<Grp, NC>(g, a, b, 0, l, ts, pd_beam_factor(a, b, l, ts), ev, uv);
+    const int lev = pd_interface_level(a, b, l, tq);
+    if (lev >= 0) pd_mode_at_interface(g, a, b, 0, lev, uv);
+    else pd_mode_at<Grp, NC>(g, a, b, 0, l, ts, pd_beam_factor(a, b, l, ts), ev, uv);
     const double* cp = a.st.colp + (long)b * PD_NCOLP;
     const double resc = cp[PD_COL_RESCALE];
     for (int i = g.lane(); i < n2; i += Grp::size) u0[((long)b * n2 + i) * a.ntau + t] = resc * uv[i];
@@ -204,8 +226,16 @@ PD_HD void pd_u0_point(const Grp& g, const PdEval& a, int b, int t, double* sm, 
 }
 
 // all Fourier modes at one point into um[NF][2n] (shared); ev: 2n scratch
+// (lev >= 0: the point is interface `lev`, pd_interface_level -- its NF * 2n radiances are contiguous in Uif)
 template <class Grp, int NC = 0>
-PD_HD void pd_all_modes_point(const Grp& g, const PdEval& a, int b, int l, double ts, double* ev, double* um) {
+PD_HD void pd_all_modes_point(const Grp& g, const PdEval& a, int b, int l, int lev, double ts, double* ev, double* um) {
+    if (lev >= 0) {
+        const int tot = a.NF * 2 * a.N;
+        const double* us = a.st.Uif + pd_uif_index(b, lev, 0, a.L, a.NF, 2 * a.N);
+        for (int i = g.lane(); i < tot; i += Grp::size) um[i] = us[i];
+        g.sync();
+        return;
+    }
     const double eb = pd_beam_factor(a, b, l, ts);
     for (int m = 0; m < a.NF; ++m) pd_mode_at<Grp, NC>(g, a, b, m, l, ts, eb, ev, um + m * 2 * a.N);
 }

@@ -43,7 +43,7 @@ __global__ void k_eval_u(PdEval a, const double* __restrict__ phi_q, int nphi, i
     const double tq = a.tau_q[pt];
     const int l = pd_locate_group(g, a.st.tau + (long)b * a.L, a.L, tq);
     const double ts = pd_scaled_tau(a, b, l, tq);
-    pd_all_modes_point<SubWarp<LANES>, NC>(g, a, b, l, ts, ev, um);
+    pd_all_modes_point<SubWarp<LANES>, NC>(g, a, b, l, pd_interface_level(a, b, l, tq), ts, ev, um);
     const double* cp = a.st.colp + (long)b * PD_NCOLP;
     const double resc = cp[PD_COL_RESCALE], phi0 = cp[PD_COL_PHI0];
     for (int idx = g.lane(); idx < n2 * nphi; idx += LANES) {

@@ -33,8 +33,12 @@ struct PdStageB {
     const double* Bv;      // [B][NF][L][2N]
     const double* dth;     // [B][L][Ns][2N]
     double* C;             // [B][NF][L][2N]
+    double* Uif;           // [B][L+1][NF][2N] stream radiances of every mode at the layer interfaces, or null
     int32_t* status;       // [B]
 };
+
+// where the 2N interface radiances of (column b, interface lev, mode m) live in Uif
+PD_HD long pd_uif_index(int b, int lev, int m, int L, int NF, int n2) { return (((long)b * (L + 1) + lev) * NF + m) * n2; }
 
 // shared-memory doubles per concurrently solved system, and history doubles per system
 PD_HD int pd_stage_b_doubles(int N) { return 3 * N * (4 * N + 1) + 8 * N + N * pd_ld(N); }
@@ -244,6 +248,28 @@ PD_HD void pd_stage_b_system(const Grp& g, const PdStageB& a, int b, int m, doub
             g.sync();
         }
         for (int i = lane; i < n2; i += Grp::size) Cout[l * n2 + i] = xs[i];
+        g.sync();
+    }
+    // interface radiances from the coefficients: u = G_l (C_l * e) + particular at the bottom of layer lev - 1 (the top
+    // of layer 0 for lev = 0) -- term by term what pd_mode_at (pd_eval.cuh) evaluates at such a point
+    for (int lev = 0; a.Uif && lev <= L; ++lev) {
+        const int l = lev > 0 ? lev - 1 : 0;
+        const double dtau = taus[l + 1] - taus[l];
+        for (int i = lane; i < n; i += Grp::size) {
+            const double e = exp(-Kc[l * n + i] * dtau);
+            vt[i] = Cout[l * n2 + i] * (lev > 0 ? e : 1.0);
+            vt[n + i] = Cout[l * n2 + n + i] * (lev > 0 ? 1.0 : e);
+        }
+        g.sync();
+        const double att = beam ? exp(-taus[lev] / mu0) : 0.0;
+        double* uo = a.Uif + pd_uif_index(b, lev, m, L, a.NF, n2);
+        for (int r = lane; r < n2; r += Grp::size) {
+            double s = 0.0;
+            for (int c = 0; c < n2; ++c) s = fma(Gat(l, r, c), vt[c], s);
+            if (beam) s = fma(Bc[l * n2 + r], att, s);
+            if (dthc) s += pd_thermal_at(dthc + (long)l * a.Ns * n2, a.Ns, n2, r, taus[lev]);
+            uo[r] = s;
+        }
         g.sync();
     }
     if (status && lane == 0) {

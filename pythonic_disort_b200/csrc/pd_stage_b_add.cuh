@@ -545,6 +545,20 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
 
     // ---------------------------------------------------------------- back sweep
     double* Cout = A.C + sys * L * N2;
+    // the interface radiances themselves (back in the unscaled basis) for the evaluation kernels
+    double rDj[NJ];
+#pragma unroll
+    PD_FOR_OWN(jj, j) rDj[jj] = 1.0 / Dj[jj];
+    auto store_interface = [&](int lev, const double (&up)[NJ], const double (&um)[NJ]) {
+        if (!A.Uif) return;
+        double* uo = A.Uif + pd_uif_index(b, lev, m, L, A.NF, N2);
+#pragma unroll
+        PD_FOR_OWN(ii, i) {
+            uo[i] = up[ii] * rDj[ii];
+            uo[N + i] = um[ii] * rDj[ii];
+        }
+    };
+    store_interface(L, ubp, ubm);
     double Qr[NJ][N], RQr[NJ][N], qi[NJ], rsi[NJ];
     auto load_history = [&](int l) {
         const double* hl = hist + (long)l * F::HIST_PER_LAYER;
@@ -576,6 +590,7 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
             utp[ii] = qi[ii] + dot_own(Qr[ii], vec);
             utm[ii] = rsi[ii] + dot_own(RQr[ii], vec);
         }
+        store_interface(l, utp, utm);
         if (l > 0) load_history(l - 1);  // in flight while this layer's coefficients are recovered
         double vrow[NJ][N], urow[NJ][N], blp[NJ], blm[NJ], El[NJ];
         eigvec_columns(Gl, vrow, urow);

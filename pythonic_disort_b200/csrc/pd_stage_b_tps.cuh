@@ -358,6 +358,23 @@ PD_HD bool pd_stage_b_tps(const PdStageB& A, int b, int m, double* hist, long hs
 
     // ---------------------------------------------------------------- back sweep
     double* Cout = A.C + sys * L * N2;
+    // the interface radiances themselves (back in the unscaled basis) for the evaluation kernels
+    double rD[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) rD[i] = 1.0 / D[i];
+    auto store_interface = [&](int lev, const double (&up)[N], const double (&um)[N]) {
+        if (!A.Uif) return;
+        double* uo = A.Uif + pd_uif_index(b, lev, m, L, A.NF, N2);
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            pd_d2 p2, m2;
+            p2.x = up[i] * rD[i]; p2.y = up[i + 1] * rD[i + 1];
+            m2.x = um[i] * rD[i]; m2.y = um[i + 1] * rD[i + 1];
+            *reinterpret_cast<pd_d2*>(uo + i) = p2;
+            *reinterpret_cast<pd_d2*>(uo + N + i) = m2;
+        }
+    };
+    store_interface(L, ubp, ubm);
     double att_b = att_t;  // exp(-tau*_L / mu0)
     for (int l = L - 1; l >= 0; --l) {
         if (l > 0) prefetch_layer(l - 1);
@@ -376,6 +393,7 @@ PD_HD bool pd_stage_b_tps(const PdStageB& A, int b, int m, double* hist, long hs
             utp[i] = a;
             utm[i] = c;
         }
+        store_interface(l, utp, utm);
         double V[N][N], U[N][N];
         eigvecs(l, V, U);
         double ptp[N], ptm[N], pbp[N], pbm[N];

@@ -87,7 +87,7 @@ int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const 
                     const double* s_s, const double* colp, const double* bpos_s, const double* bneg_s,
                     const double* pmu0, const double* mu_nodes, const double* w_nodes, const double* ptab,
                     const double* bdrf_q, const double* bdrf_q0, void* workspace, size_t, double* K, double* G,
-                    double* Bv, double* dth, double* C, int32_t* status, void*) {
+                    double* Bv, double* dth, double* C, double* Uif, int32_t* status, void*) {
     const int N = cfg->NQuad / 2;
     if (stages & PD_STAGE_EIGEN) memset(status, 0, sizeof(int32_t) * cfg->B);
     PdStageA a;
@@ -133,7 +133,7 @@ int pd_solve_stages(const pd_config* cfg, int stages, const double* taus, const 
     sb.NFb = cfg->NFb; sb.beam = a.beam; sb.iso = a.iso; sb.bdrf_percol = (cfg->flags & PD_FLAG_BDRF_PERCOL) != 0;
     sb.taus = taus; sb.colp = colp; sb.bpos = bpos_s; sb.bneg = bneg_s; sb.mu = mu_nodes; sb.w = w_nodes;
     sb.bdrf_q = bdrf_q; sb.bdrf_q0 = bdrf_q0; sb.K = K; sb.G = G; sb.RT = nullptr; sb.Bv = Bv; sb.dth = dth; sb.C = C;
-    sb.status = status;
+    sb.Uif = Uif; sb.status = status;
     double* smb = (double*)malloc(sizeof(double) * (pd_stage_b_doubles(N) + 16));
     // same dispatch as pd_launch_stage_b: interface-radiance elimination for N = 2, 4 (thread per system), 8, 16 (unless
     // PD_FLAG_GENERIC_KERNELS), pivoted band solver otherwise and for the systems the first one hands back
@@ -161,9 +161,9 @@ int pd_solve(const pd_config* cfg, const double* taus, const double* omega_s, co
              const double* colp, const double* bpos_s, const double* bneg_s, const double* pmu0,
              const double* mu_nodes, const double* w_nodes, const double* ptab, const double* bdrf_q,
              const double* bdrf_q0, void* workspace, size_t wsb, double* K, double* G, double* Bv, double* dth, double* C,
-             int32_t* status, void* stream) {
+             double* Uif, int32_t* status, void* stream) {
     return pd_solve_stages(cfg, PD_STAGE_EIGEN | PD_STAGE_BC, taus, omega_s, wleg, s_s, colp, bpos_s, bneg_s, pmu0,
-                           mu_nodes, w_nodes, ptab, bdrf_q, bdrf_q0, workspace, wsb, K, G, Bv, dth, C, status, stream);
+                           mu_nodes, w_nodes, ptab, bdrf_q, bdrf_q0, workspace, wsb, K, G, Bv, dth, C, Uif, status, stream);
 }
 
 static PdEval make_eval(const pd_config* cfg, const pd_state* st, const double* tau_q, int ntau, int anti) {
@@ -222,7 +222,7 @@ int pd_eval_u(const pd_config* cfg, const pd_state* st, const double* tau_q, int
             const double tq = tau_q[(long)b * ntau + t];
             const int l = pd_locate(st->tau + (long)b * L, L, tq);
             const double ts = pd_scaled_tau(a, b, l, tq);
-            pd_all_modes_point(g, a, b, l, ts, ev, um);
+            pd_all_modes_point(g, a, b, l, pd_interface_level(a, b, l, tq), ts, ev, um);
             for (int i = 0; i < n2; ++i) {
                 for (int q = 0; q < nphi; ++q) {
                     double v = resc * pd_azimuth_sum(um + i, n2, a.NF, phi0 - phi_q[q]);

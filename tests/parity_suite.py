@@ -207,6 +207,72 @@ def check_ensemble_vs_live_oracle(pydisort, name, ncol, first, pool=None):
     return compare_fields(got, runs[0], ncol, tol, name, sens=sens)
 
 
+def _solution_of(out_fn):
+    """The solved state an output closure of pydisort() holds (test access to switch its interface table off)."""
+    for cell in out_fn.__closure__ or ():
+        if type(cell.cell_contents).__name__ == "_Solution":
+            return cell.cell_contents
+    raise AssertionError("output function holds no _Solution")
+
+
+def check_interface_levels_vs_assembled(pydisort, name, ncol, first=0, tol=1e-10, typical=1e-11):
+    """Query points that are layer interfaces are answered from the interface radiances of the boundary-condition
+    sweep (pd_state.Uif), every other point from G (C * exp) + particular.  Both formulations on the same levels
+    (the second with the table switched off) and a grid mixing interfaces with interior points: the median column
+    agrees to ``typical`` (measured 1e-14 at NQuad = 16, 4e-12 at NQuad = 32 with 100 layers) and every column to ``tol``, ten times inside the parity bar (measured
+    worst 2.5e-11, SW column 3163, where an eigenvalue lies 4e-8 from 1/mu0 and the beam particular solution is
+    conditioned like 1/(1/mu0^2 - k^2): there the two formulations are 2.9e-11 and 1.7e-11 from the oracle).  A
+    self-consistency test of the CUDA path, not a parity test (the goldens and the oracle runs exercise the interface
+    path through the ensembles' level grids)."""
+    ens = synthetic.make(name, ncol, first)
+    t_if = np.asarray(ens["tau_eval"], dtype=np.float64)
+    tau = np.asarray(ens["args"][0], dtype=np.float64)
+    if tau.ndim == 1:
+        tau = np.tile(tau, (ncol, 1))
+    if t_if.ndim == 1:
+        t_if = np.tile(t_if, (ncol, 1))
+    edges = np.concatenate([np.zeros((ncol, 1)), tau], axis=1)
+    mids = 0.5 * (edges[:, :-1] + edges[:, 1:])
+    mixed = np.sort(np.concatenate([edges, mids[:, ::3]], axis=1), axis=1)
+    hits = np.mean(np.isin(t_if, edges))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = pydisort(*ens["args"], **ens["kwargs"])
+    sol = _solution_of(out[1])
+    assert sol.Uif is not None
+
+    def evaluate(t):
+        dn = out[2](t)
+        res = dict(flux_up=to_np(out[1](t)), flux_down_diffuse=to_np(dn[0]), u0=to_np(out[3](t)))
+        if "u" in ens["outputs"]:
+            res["u"] = to_np(out[4](t, ens["phi_eval"]))
+        return res
+
+    grids = [edges, mixed] + ([t_if] if hits < 1.0 else [])
+    with_table = [evaluate(t) for t in grids]
+    table, sol.Uif = sol.Uif, None
+    try:
+        assembled = [evaluate(t) for t in grids]
+    finally:
+        sol.Uif = table
+    worst = 0.0
+    for a, c in zip(with_table, assembled):
+        for key in a:
+            errs = [np.max(np.abs(a[key][b] - c[key][b])) / np.max(np.abs(c[key][b])) for b in range(ncol)]
+            worst = max(worst, max(errs))
+            assert max(errs) <= tol and np.median(errs) <= typical, (name, key, int(np.argmax(errs)), max(errs), np.median(errs))
+    # the table must actually have been used: with it, interface levels no longer depend on C
+    keep = sol.C.clone()
+    sol.C.zero_()
+    try:
+        again = evaluate(edges)
+    finally:
+        sol.C.copy_(keep)
+    for key in again:
+        assert np.array_equal(again[key], with_table[0][key]), key
+    return worst
+
+
 def check_actinic_vs_golden(pd_module, tol=1e-9):
     """Row a13: ``generate_diff_act_flux_funcs`` (subroutines.py:258-318) on this package's ``u0`` -- including the
     delta-scaling reclassification term of ``_assemble_intensity_and_fluxes.py:360-371`` -- against the reference's

@@ -26,12 +26,12 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(path)
     for name in declared_functions():
         assert hasattr(lib, name), name
-    assert _lib.bind(path).pd_abi_version() == 1
+    assert _lib.bind(path).pd_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.pd_config) == 10 * 4
-    assert ctypes.sizeof(_lib.pd_state) == 11 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_lib.pd_state) == 12 * ctypes.sizeof(ctypes.c_void_p)
 
 
 def test_workspace_query_and_argument_validation_need_no_gpu():

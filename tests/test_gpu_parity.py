@@ -215,6 +215,13 @@ def test_production_kernels_agree_with_the_generic_ones_on_large_slices(name, nc
     assert worst < tol
 
 
+@pytest.mark.parametrize("name,ncol,first", [("sw", 512, 3000), ("lw", 4096, 7000), ("ha", 48, 900), ("tp1", 6, 0), ("tp9c", 2, 0)])
+def test_interface_levels_come_from_the_sweep_and_agree_with_the_assembled_solution(name, ncol, first):
+    """Levels that are layer interfaces are read from the sweep's interface radiances (pd_state.Uif); the same
+    levels assembled from G, C, and grids that mix interfaces with interior points, agree to 1e-11 of scale."""
+    parity_suite.check_interface_levels_vs_assembled(pd.pydisort, name, ncol, first)
+
+
 def test_unphysical_phase_function_is_flagged_not_crashed():
     """Moments that make the reduced matrices indefinite: the symmetric path must hand the item to the general
     solver, which reports the non-positive k^2 (the reference returns NaN / complex garbage here)."""
