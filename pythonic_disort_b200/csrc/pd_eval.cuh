@@ -152,6 +152,29 @@ PD_HD void pd_mode_at(const Grp& g, const PdEval& a, int b, int m, int l, double
     g.sync();
 }
 
+// flux outputs of one point from the hemispheric sums up = sum_i mu_i w_i u_i, dn = sum_i mu_i w_i u_{n+i}  (:446-613)
+PD_HD void pd_flux_store(const PdEval& a, int b, int t, int l, double tq, double ts, double up, double dn, double* Fup,
+                         double* Fdn, double* Fdir) {
+    const double* cp = a.st.colp + (long)b * PD_NCOLP;
+    const double resc = cp[PD_COL_RESCALE];
+    double direct = 0.0, direct_s = 0.0;
+    if (a.beam && cp[PD_COL_I0] > 0.0) {
+        const double mu0 = cp[PD_COL_MU0], I0 = cp[PD_COL_I0];
+        if (a.anti) {
+            const double sc = a.st.scale_tau[(long)b * a.L + l];
+            direct = I0 * mu0 * exp(-tq / mu0) * -mu0;
+            direct_s = I0 * mu0 * exp(-ts / mu0) / (-sc / mu0);
+        } else {
+            direct = I0 * mu0 * exp(-tq / mu0);
+            direct_s = I0 * mu0 * exp(-ts / mu0);
+        }
+    }
+    const long o = (long)b * a.ntau + t;
+    Fup[o] = resc * (2.0 * PD_PI * up);
+    Fdn[o] = resc * (2.0 * PD_PI * dn + direct_s - direct);
+    Fdir[o] = resc * direct;
+}
+
 // fluxes at one point (:446-613).  sm: 4n doubles.
 template <class Grp, int NC = 0>
 PD_HD void pd_flux_point(const Grp& g, const PdEval& a, int b, int t, double* sm, double* Fup, double* Fdn,
@@ -172,26 +195,44 @@ PD_HD void pd_flux_point(const Grp& g, const PdEval& a, int b, int t, double* sm
             up = fma(mw, uv[i], up);
             dn = fma(mw, uv[n + i], dn);
         }
-        const double* cp = a.st.colp + (long)b * PD_NCOLP;
-        const double resc = cp[PD_COL_RESCALE];
-        double direct = 0.0, direct_s = 0.0;
-        if (a.beam && cp[PD_COL_I0] > 0.0) {
-            const double mu0 = cp[PD_COL_MU0], I0 = cp[PD_COL_I0];
-            if (a.anti) {
-                const double sc = a.st.scale_tau[(long)b * a.L + l];
-                direct = I0 * mu0 * exp(-tq / mu0) * -mu0;
-                direct_s = I0 * mu0 * exp(-ts / mu0) / (-sc / mu0);
-            } else {
-                direct = I0 * mu0 * exp(-tq / mu0);
-                direct_s = I0 * mu0 * exp(-ts / mu0);
-            }
-        }
-        const long o = (long)b * a.ntau + t;
-        Fup[o] = resc * (2.0 * PD_PI * up);
-        Fdn[o] = resc * (2.0 * PD_PI * dn + direct_s - direct);
-        Fdir[o] = resc * direct;
+        pd_flux_store(a, b, t, l, tq, ts, up, dn, Fup, Fdn, Fdir);
     }
     g.sync();
+}
+
+// The same for a point that is a layer interface, by ONE thread (no scratch): the 2n radiances of mode 0 are one
+// contiguous record of Uif, and consecutive levels of a column are consecutive records.  Returns false (nothing
+// written) if the point is not an interface; sums in the order of pd_flux_point, so both give the same bits.
+template <int NC = 0>
+PD_HD bool pd_flux_point_interface(const PdEval& a, int b, int t, double* Fup, double* Fdn, double* Fdir) {
+    const int n = NC > 0 ? NC : a.N;
+    const double tq = a.tau_q[(long)b * a.ntau + t];
+    const double* tau = a.st.tau + (long)b * a.L;
+    // a level grid that mirrors the layers (ntau = L + 1: 0, tau_0, .., tau_{L-1}) is found without a search
+    int l = (t > 0 && t <= a.L && tau[t - 1] == tq) ? t - 1 : pd_locate(tau, a.L, tq);
+    const int lev = pd_interface_level(a, b, l, tq);
+    if (lev < 0) return false;
+    const double* us = a.st.Uif + pd_uif_index(b, lev, 0, a.L, a.NF, 2 * n);
+    double up = 0.0, dn = 0.0;
+    if (NC > 0 && NC % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < (NC > 0 ? NC : 2); i += 2) {
+            const pd_d2 p2 = *reinterpret_cast<const pd_d2*>(us + i), m2 = *reinterpret_cast<const pd_d2*>(us + n + i);
+            const double w0 = a.st.mu_nodes[i] * a.st.w_nodes[i], w1 = a.st.mu_nodes[i + 1] * a.st.w_nodes[i + 1];
+            up = fma(w0, p2.x, up);
+            dn = fma(w0, m2.x, dn);
+            up = fma(w1, p2.y, up);
+            dn = fma(w1, m2.y, dn);
+        }
+    } else {
+        for (int i = 0; i < n; ++i) {
+            const double mw = a.st.mu_nodes[i] * a.st.w_nodes[i];
+            up = fma(mw, us[i], up);
+            dn = fma(mw, us[n + i], dn);
+        }
+    }
+    pd_flux_store(a, b, t, l, tq, pd_scaled_tau(a, b, l, tq), up, dn, Fup, Fdn, Fdir);
+    return true;
 }
 
 // u0 at one point (:334-433); recl = actinic delta-scaling reclassification term (:360-371)

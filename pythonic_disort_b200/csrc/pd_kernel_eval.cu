@@ -7,14 +7,31 @@
 // ============================================================================
 // evaluation kernels
 // ============================================================================
+// A warp takes 32 consecutive points.  If every one of them is a layer interface (the usual level grid), each lane
+// finishes its own point from the interface radiances -- one contiguous record per point, no shared memory, no
+// cooperation.  Otherwise the warp's points go through the lane-group routine, LANES lanes per point.
 template <int LANES, int NC>
 __global__ void k_eval_flux(PdEval a, double* Fup, double* Fdn, double* Fdir) {
     extern __shared__ double smem[];
-    const int gpc = blockDim.x / LANES, gi = threadIdx.x / LANES;
-    const long pt = (long)blockIdx.x * gpc + gi;
-    if (pt >= (long)a.B * a.ntau) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long pts = (long)a.B * a.ntau;
+    const long p0 = ((long)blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+    if (p0 >= pts) return;
+    const long mine = p0 + lane;
+    bool done = true;
+    if (a.st.Uif && !a.anti) {
+        if (mine < pts) done = pd_flux_point_interface<NC>(a, (int)(mine / a.ntau), (int)(mine % a.ntau), Fup, Fdn, Fdir);
+    } else {
+        done = false;
+    }
+    if (__all_sync(0xffffffffu, done)) return;
     SubWarp<LANES> g;
-    pd_flux_point<SubWarp<LANES>, NC>(g, a, (int)(pt / a.ntau), (int)(pt % a.ntau), smem + (long)gi * 4 * a.N, Fup, Fdn, Fdir);
+    constexpr int GPW = 32 / LANES;  // points per pass of the warp
+    double* sm = smem + (long)(warp * GPW + lane / LANES) * 4 * a.N;
+    for (int k = 0; k < LANES; ++k) {
+        const long pt = p0 + k * GPW + lane / LANES;
+        if (pt < pts) pd_flux_point<SubWarp<LANES>, NC>(g, a, (int)(pt / a.ntau), (int)(pt % a.ntau), sm, Fup, Fdn, Fdir);
+    }
 }
 
 template <int LANES, int NC>
@@ -394,7 +411,7 @@ int pd_eval_flux(const pd_config* cfg, const pd_state* st, const double* tau_q, 
     const int lanes = pd_lanes_for(a.N), threads = 128, gpc = threads / lanes;
     const long pts = (long)a.B * ntau;
     const size_t smem = (size_t)gpc * 4 * a.N * 8;
-    const unsigned grid = (unsigned)((pts + gpc - 1) / gpc);
+    const unsigned grid = (unsigned)((pts + threads - 1) / threads);  // a point per thread (k_eval_flux)
     PD_DISPATCH_N(a.N, (k_eval_flux<LN, NC><<<grid, threads, smem, pd_stream(stream)>>>(a, Fup, Fdn_diffuse, Fdn_direct)));
     return (int)cudaGetLastError();
 }

@@ -9,7 +9,7 @@
 // (alpha-beta)(alpha+beta) = X' S (_solve_for_gen_and_part_sols.py:179-183) becomes a symmetric one:
 //     S = L L^T (Cholesky),  T = L^T X' L,  T W = W diag(k^2),  W orthogonal,
 //     eigenvectors V^ = L^-T W,   U^ = (alpha+beta)^ V^ / k = -L W / k = -L L^T V^ / k,   (V^)^-1 = W^T L^T = V^T L L^T.
-// T is diagonalised by cyclic Jacobi rotations: no data-dependent branches or indices, so 32 items
+// T is diagonalised by cyclic Jacobi rotations (odd-even transposition ordering): no data-dependent branches or indices, so 32 items
 // run in lock-step in one warp with all matrices in registers, and Jacobi delivers the small
 // eigenvalues (omega* -> 1) to high relative accuracy.  The particular solutions reuse the
 // decomposition instead of LU factorisations:
@@ -23,7 +23,8 @@
 
 #define PD_JACOBI_MAX_SWEEPS 12
 #ifndef PD_JACOBI_GROUP
-#define PD_JACOBI_GROUP 2  // rotations of a round whose parameters are computed together (divides N/2)
+#define PD_JACOBI_GROUP 4  // rotations of a step whose parameters are computed together (N = 8: all of them; measured
+                           // 70.4 -> 68.7 ms per SW step against groups of two, and fewer spills)
 #endif
 
 template <int N>
@@ -33,12 +34,6 @@ struct PdSym {
     PD_HD static constexpr int idx(int i, int j) {  // upper-packed index of (i, j), any order
         return (i <= j) ? (i * N - i * (i - 1) / 2 + (j - i)) : (j * N - j * (j - 1) / 2 + (i - j));
     }
-    // round-robin tournament (circle method): round r = 0 .. N-2, game g = 0 .. N/2-1; the N/2 pairs of a round are
-    // disjoint and the N-1 rounds cover every pair once.  rr_p < rr_q.
-    PD_HD static constexpr int rr_a(int r, int g) { return (g == 0) ? N - 1 : (r + g) % (N - 1); }
-    PD_HD static constexpr int rr_b(int r, int g) { return (g == 0) ? r : (r - g + (N - 1)) % (N - 1); }
-    PD_HD static constexpr int rr_p(int r, int g) { return rr_a(r, g) < rr_b(r, g) ? rr_a(r, g) : rr_b(r, g); }
-    PD_HD static constexpr int rr_q(int r, int g) { return rr_a(r, g) < rr_b(r, g) ? rr_b(r, g) : rr_a(r, g); }
 };
 
 // sm: per-thread parking area with stride `ps` between consecutive doubles of one thread
@@ -227,56 +222,68 @@ PD_HD bool pd_stage_a_sym_item(const PdStageA& a, int b, int m, int l, const dou
 #else
         if (converged || !ok) break;
 #endif
-        // Round-robin ("tournament") ordering: the N/2 rotations of a round act on disjoint index pairs, so the
-        // parameters of GRP = min(PD_JACOBI_GROUP, N/2) of them are computed together from the same T -- their rsqrt / rcp chains
-        // (about 200 cycles each, far longer than the 14 row/column pair updates they feed) overlap instead of
-        // serialising -- and the rotations are then applied one after the other.
+        // Odd-even transposition ordering (Brent-Luk): even steps rotate the index pairs (0,1), (2,3), ..., odd steps
+        // (1,2), (3,4), ...; after its rotation a pair trades places, so that in N steps every index has met every
+        // other one exactly once (N (N-1) / 2 rotations, one sweep).  The exchange costs nothing -- it is the same pair
+        // update with the two results written to each other's place -- and the pairs of a step are the same in
+        // every step of that parity: the code of a sweep is ONE even + ONE odd step in a loop that stays rolled
+        // (N = 8: 7 rotations, 12 KB, instead of 28 rotations unrolled over the 7 rounds of a round-robin tournament,
+        // whose 150 KB per sweep went through the instruction cache once per sweep: 1.1 fetch stalls per issue).
+        // The rotations of a step act on disjoint pairs, so the parameters of GRP = min(PD_JACOBI_GROUP, N/2) of them
+        // are computed together from the same T -- their rsqrt / rcp chains (about 200 cycles each, far longer than
+        // the 14 row/column pair updates they feed) overlap instead of serialising.
+        // An item that has converged is frozen: its "rotation" is the quarter turn, which with the exchange leaves
+        // both indices in place and flips one sign (a similarity transform; all later arithmetic is sign-symmetric),
+        // so its results do not depend on which other items share its warp.
+#pragma unroll 1
+        for (int step2 = 0; step2 < N / 2; ++step2)
 #pragma unroll
-        for (int rnd = 0; rnd < N - 1; ++rnd)
+            for (int par = 0; par < 2; ++par)
 #pragma unroll
-            for (int g0 = 0; g0 < N / 2; g0 += GRP) {
-                double cc[GRP], ss[GRP], tt[GRP];
-                bool tny[GRP];
+                for (int g0 = 0; g0 < N / 2 - par; g0 += GRP) {
+                    double cc[GRP], ss[GRP], tt[GRP];
+                    bool tny[GRP];
 #pragma unroll
-                for (int gi = 0; gi < GRP; ++gi) {
-                    const int p = P::rr_p(rnd, g0 + gi), q = P::rr_q(rnd, g0 + gi);
-                    const double apq = T[P::idx(p, q)], app = T[P::idx(p, p)], aqq = T[P::idx(q, q)];
-                    // rotation that annihilates T(p,q); identity if it is already negligible
-                    // t = tan(rotation angle) = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq),
-                    // written without the division by apq:  t = sgn(d) 2 apq / (|d| + sqrt(d^2 + 4 apq^2)).
-                    // (an item that has converged is frozen, so its result does not depend on its warp neighbours)
-                    const bool tiny = converged || (apq * apq <= 1e-36 * fabs(app * aqq));
-                    const double d = aqq - app, a2 = 2.0 * apq;
-                    const double h = fma(d, d, a2 * a2);
-                    const double den = fabs(d) + h * pd_rsqrt(h > 0.0 ? h : 1.0);
-                    const double tn = tiny ? 0.0 : ((d >= 0.0) ? a2 : -a2) * pd_rcp(den > 0.0 ? den : 1.0);
-                    const double c = pd_rsqrt(fma(tn, tn, 1.0));
-                    cc[gi] = c;
-                    ss[gi] = tn * c;
-                    tt[gi] = tn;
-                    tny[gi] = tiny;
-                }
+                    for (int gi = 0; gi < GRP; ++gi) {
+                        if (g0 + gi >= N / 2 - par) continue;
+                        const int p = 2 * (g0 + gi) + par, q = p + 1;
+                        const double apq = T[P::idx(p, q)], app = T[P::idx(p, p)], aqq = T[P::idx(q, q)];
+                        // rotation that annihilates T(p,q); identity if it is already negligible
+                        // t = tan(rotation angle) = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq),
+                        // written without the division by apq:  t = sgn(d) 2 apq / (|d| + sqrt(d^2 + 4 apq^2)).
+                        const bool tiny = (apq * apq <= 1e-36 * fabs(app * aqq));
+                        const double d = aqq - app, a2 = 2.0 * apq;
+                        const double h = fma(d, d, a2 * a2);
+                        const double den = fabs(d) + h * pd_rsqrt(h > 0.0 ? h : 1.0);
+                        const double tn = tiny ? 0.0 : ((d >= 0.0) ? a2 : -a2) * pd_rcp(den > 0.0 ? den : 1.0);
+                        const double c = pd_rsqrt(fma(tn, tn, 1.0));
+                        cc[gi] = converged ? 0.0 : c;
+                        ss[gi] = converged ? 1.0 : tn * c;
+                        tt[gi] = tn;
+                        tny[gi] = tiny;
+                    }
 #pragma unroll
-                for (int gi = 0; gi < GRP; ++gi) {
-                    const int p = P::rr_p(rnd, g0 + gi), q = P::rr_q(rnd, g0 + gi);
-                    const double c = cc[gi], s = ss[gi], tn = tt[gi];
-                    const double apq = T[P::idx(p, q)], app = T[P::idx(p, p)], aqq = T[P::idx(q, q)];
-                    T[P::idx(p, p)] = fma(-tn, apq, app);
-                    T[P::idx(q, q)] = fma(tn, apq, aqq);
-                    T[P::idx(p, q)] = tny[gi] ? apq : 0.0;
+                    for (int gi = 0; gi < GRP; ++gi) {
+                        if (g0 + gi >= N / 2 - par) continue;
+                        const int p = 2 * (g0 + gi) + par, q = p + 1;
+                        const double c = cc[gi], s = ss[gi], tn = tt[gi];
+                        const double apq = T[P::idx(p, q)], app = T[P::idx(p, p)], aqq = T[P::idx(q, q)];
+                        T[P::idx(p, p)] = converged ? app : fma(tn, apq, aqq);   // rotated, then exchanged
+                        T[P::idx(q, q)] = converged ? aqq : fma(-tn, apq, app);
+                        T[P::idx(p, q)] = converged ? -apq : (tny[gi] ? apq : 0.0);
 #pragma unroll
-                    for (int r = 0; r < N; ++r) {
-                        if (r != p && r != q) {
-                            const double trp = T[P::idx(r, p)], trq = T[P::idx(r, q)];
-                            T[P::idx(r, p)] = fma(c, trp, -s * trq);
-                            T[P::idx(r, q)] = fma(s, trp, c * trq);
+                        for (int r = 0; r < N; ++r) {
+                            if (r != p && r != q) {
+                                const double trp = T[P::idx(r, p)], trq = T[P::idx(r, q)];
+                                T[P::idx(r, p)] = fma(s, trp, c * trq);
+                                T[P::idx(r, q)] = fma(c, trp, -s * trq);
+                            }
+                            const double wp = W[r * N + p], wq = W[r * N + q];
+                            W[r * N + p] = fma(s, wp, c * wq);
+                            W[r * N + q] = fma(c, wp, -s * wq);
                         }
-                        const double wp = W[r * N + p], wq = W[r * N + q];
-                        W[r * N + p] = fma(c, wp, -s * wq);
-                        W[r * N + q] = fma(s, wp, c * wq);
                     }
                 }
-            }
     }
     double k[N], kinv[N];
 #pragma unroll

@@ -181,7 +181,9 @@ int pd_eval_flux(const pd_config* cfg, const pd_state* st, const double* tau_q, 
     SerialGroup g;
     double* sm = (double*)malloc(sizeof(double) * 4 * a.N);
     for (int b = 0; b < a.B; ++b)
-        for (int t = 0; t < ntau; ++t) pd_flux_point(g, a, b, t, sm, Fup, Fdn_diffuse, Fdn_direct);
+        for (int t = 0; t < ntau; ++t)  // as k_eval_flux: the one-thread interface routine first, the group routine otherwise
+            if (!(a.st.Uif && !a.anti && pd_flux_point_interface<0>(a, b, t, Fup, Fdn_diffuse, Fdn_direct)))
+                pd_flux_point(g, a, b, t, sm, Fup, Fdn_diffuse, Fdn_direct);
     free(sm);
     return 0;
 }

@@ -46,7 +46,7 @@ def test_ensemble_slices_vs_live_oracle(name, ncol, first):
     parity_suite.check_ensemble_vs_live_oracle(pd.pydisort, name, ncol, first)
 
 
-@pytest.mark.parametrize("name,ncol", [("sw", 3), ("lw", 8), ("ha", 1), ("tp9c", 2)])
+@pytest.mark.parametrize("name,ncol", [("sw", 3), ("lw", 8), ("ha", 1), ("tp9c", 2), ("tp1", 6)])
 def test_interface_levels_come_from_the_sweep_and_agree_with_the_assembled_solution(name, ncol):
     parity_suite.check_interface_levels_vs_assembled(pd.pydisort, name, ncol)
 
