@@ -13,7 +13,12 @@ rank owns its own 65,536 columns).
 
 value : columns/s, inputs resident in HBM, outputs left in HBM (CUDA events, max over ranks).
 e2e   : columns/s through the package's one-call host interface, pythonic_disort_b200.ensemble.solve_ensemble():
-        pinned HOST inputs -> HOST outputs, every H2D / D2H byte inside the timed region.
+        pinned HOST inputs -> HOST outputs, every H2D / D2H byte inside the timed region.  Inputs are the
+        reference-shaped arrays (Leg_coeffs_all [B, L, NLeg_all], s_poly_coeffs [B, L, 2], ...).
+e2e_compact_inputs : the same call with the inputs that have a per-layer description passed as such
+        (inputs.HenyeyGreenstein: asymmetry parameters, inputs.LevelSource: level values of the thermal source) and
+        expanded on the device: what the link-bound LW ensemble reaches when the host ships 242 instead of 844 doubles
+        per column.  Reported beside `e2e`, never in its place.
 roofline : the dominant kernel's algorithmic FP64 FLOP/s (SURVEY 8(d) counts) against the FP64 FMA peak measured in
         this run by pd_fp64_probe (MEASURED_PEAKS.json has no FP64 entry); peak_dfma / peak_dmma are both given;
         `hbm` is the same kernel against MEASURED_PEAKS.json:hbm_gbs; `traffic` is the ncu DRAM byte count of that
@@ -269,7 +274,8 @@ class Bench:
             if total <= 65536:
                 full = make_inputs(wl["ens"], total, 0, only_flux)
                 a, k, _ = parallel.shard_inputs(total, full["args"], full["kwargs"], self.rank, self.world)
-                ens = dict(full, args=a, kwargs=k, B=hi - lo, tau_eval=full["tau_eval"][lo:hi])
+                ens = dict(full, args=a, kwargs=k, B=hi - lo, tau_eval=full["tau_eval"][lo:hi],
+                           compact={n: v[lo:hi] for n, v in full.get("compact", {}).items()})
             else:    # too big to build on every rank: the generator's subset property gives the same columns
                 ens = make_inputs(wl["ens"], hi - lo, lo, only_flux)
             cols_total = total
@@ -332,33 +338,54 @@ class Bench:
         torch.cuda.empty_cache()
 
         # ---- end-to-end arm: the package's host interface (pinned host inputs -> host outputs) ----
-        host_args = [ensemble.pinned(a) if isinstance(a, np.ndarray) else a for a in ens["args"]]
-        host_kw = {k: ([ensemble.pinned(m) if isinstance(m, np.ndarray) else m for m in v] if k == "BDRF_Fourier_modes"
-                       else (ensemble.pinned(v) if isinstance(v, np.ndarray) else v)) for k, v in ens["kwargs"].items()}
+        def pin(x):
+            if isinstance(x, api.DeviceInput):
+                return x.with_parts(tuple(pin(p) for p in x.parts()))
+            return ensemble.pinned(x) if isinstance(x, np.ndarray) else x
+
         host_tau = ensemble.pinned(ens["tau_eval"])
-        results = [None, None]   # two sets of pinned output buffers: step k+1 is enqueued while step k drains
 
-        def step_e2e(k):
-            cur = ensemble.solve_ensemble(*host_args, tau=host_tau, phi=phi, mu=mu_user, outputs=outputs,
-                                          chunk=chunk_e2e, out=results[k % 2], wait=False, **host_kw)
-            prev = results[(k + 1) % 2]
-            if prev is not None:
-                prev.wait()   # step k - 1 has reached the host (its deferred checks are raised here)
-            results[k % 2] = cur
+        def e2e_arm(args_in, kw_in):
+            host_args = [pin(a) for a in args_in]
+            host_kw = {k: ([pin(m) for m in v] if k == "BDRF_Fourier_modes" else pin(v)) for k, v in kw_in.items()}
+            results = [None, None]   # two sets of pinned output buffers: step k+1 is enqueued while step k drains
 
-        def drain():
-            for r in results:
-                if r is not None:
-                    r.wait()
+            def step_e2e(k):
+                cur = ensemble.solve_ensemble(*host_args, tau=host_tau, phi=phi, mu=mu_user, outputs=outputs,
+                                              chunk=chunk_e2e, out=results[k % 2], wait=False, **host_kw)
+                prev = results[(k + 1) % 2]
+                if prev is not None:
+                    prev.wait()   # step k - 1 has reached the host (its deferred checks are raised here)
+                results[k % 2] = cur
 
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            step_e2e(0)
-            step_e2e(1)
-            drain()
-            ms_e2e = self.timed(steps, step_e2e, drain)
-        h2d, d2h = results[0].h2d_bytes, results[0].d2h_bytes
-        del results, host_args, host_kw
+            def drain():
+                for r in results:
+                    if r is not None:
+                        r.wait()
+
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                step_e2e(0)
+                step_e2e(1)
+                drain()
+                ms = self.timed(steps, step_e2e, drain)
+            return ms, results[0].h2d_bytes, results[0].d2h_bytes
+
+        ms_e2e, h2d, d2h = e2e_arm(ens["args"], ens["kwargs"])
+        # the same ensemble with the inputs that have one described per layer (Henyey-Greenstein asymmetry parameters,
+        # level values of the thermal source) instead of as arrays: pydisort() expands them on the device (inputs.py)
+        e2e_compact = None
+        if ens.get("compact"):
+            cargs, ckw = list(ens["args"]), dict(ens["kwargs"])
+            for name, obj in ens["compact"].items():
+                if name in api.POSITIONAL:
+                    cargs[api.POSITIONAL.index(name)] = obj
+                else:
+                    ckw[name] = obj
+            ms_c, h2d_c, d2h_c = e2e_arm(cargs, ckw)
+            e2e_compact = {"value": cols_total / (ms_c / steps * 1e-3), "unit": "columns/s", "h2d_bytes_per_step": h2d_c,
+                           "d2h_bytes_per_step": d2h_c, "inputs": {n: type(o).__name__ for n, o in ens["compact"].items()},
+                           "api": "pythonic_disort_b200.ensemble.solve_ensemble"}
 
         ms_step = ms_dev / steps
         value = cols_total / (ms_step * 1e-3)
@@ -409,6 +436,7 @@ class Bench:
             "config": workload_config(workload, cols_total, B, chunk, chunk_e2e),
             "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "pythonic_disort_b200.ensemble.solve_ensemble"},
+            "e2e_compact_inputs": e2e_compact,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }
 
@@ -428,7 +456,8 @@ def run_gpu(args):
         plan = [("lw", True, 3, 3), ("ha", True, 1, 3), ("sw_flux", False, 3, 3), ("tp1", False, 3, 3), ("tp9c", False, 3, 3)]
         for name, strong_o, st, wu in plan:
             r = bench.run(name, st, wu, strong_o, 0, 0, min(args.cpu_seconds, 5.0), not args.no_cpu, pool)
-            keep = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "scaling", "e2e", "cpu_baseline", "gpu_launches")}
+            keep = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "scaling", "e2e", "e2e_compact_inputs", "cpu_baseline",
+                                      "gpu_launches")}
             keep["config"] = {k: r["config"][k] for k in ("description", "columns_total", "columns_per_gpu", "chunk_columns",
                                                            "chunk_columns_e2e")}
             rf = r["roofline"]

@@ -216,6 +216,18 @@ int pd_planck_band(long n, const double* T, double wvnmlo, double wvnmhi, const 
 int pd_s_poly_coeffs(int B, int L, const double* tau, const double* temper, double wvnmlo, double wvnmhi,
                      const double* gl16, double* s_poly, void* stream);
 
+/* Inputs a caller describes by a few numbers per layer, expanded on the device so that the host -> device link carries
+ * the description only ("callers either side of the path"; used by pydisort() / solve_ensemble() for the
+ * HenyeyGreenstein and LevelSource input objects of pythonic_disort_b200.api):
+ * pd_hg_moments   : phase-function moments of Henyey-Greenstein layers, the `Leg_coeffs_all` input the reference's users
+ *                   build as g ** np.arange(NLeg_all) (pydisotest/4_test.py:27, 5_test.py:24):  g[n] -> out[n][NLeg_all],
+ *                   out[i][k] = pow(g[i], k) (within 2 ulp of numpy's result), out[i][0] = 1.
+ * pd_level_source : `s_poly_coeffs` of a thermal source that is linear in tau inside every layer, from its values at the
+ *                   L + 1 levels -- the second half of generate_s_poly_coeffs (subroutines.py:440-454), for callers who
+ *                   hold band emissions rather than temperatures:  tau[B][L], lev[B][L+1] -> s_poly[B][L][2]. */
+int pd_hg_moments(long n, int NLeg_all, const double* g, double* out, void* stream);
+int pd_level_source(int B, int L, const double* tau, const double* lev, double* s_poly, void* stream);
+
 /* Surface input on the device: Fourier modes m < NF of the Hapke BDRF of DISORT's test problems
  * (pydisotest/6_test.py:11-24) in the relative azimuth, as the reference's users compute them with quad_vec
  * (pydisotest/6_test.py:193-201) before handing them to pydisort() / cache_BDRF_Fourier_modes (subroutines.py:490-570):

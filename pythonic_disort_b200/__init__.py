@@ -11,4 +11,11 @@ def pydisort(*args, **kwargs):
     return _impl(*args, **kwargs)
 
 
-__all__ = ["pydisort", "subroutines"]
+def __getattr__(name):  # HenyeyGreenstein, LevelSource: inputs expanded on the device (inputs.py)
+    if name in ("HenyeyGreenstein", "LevelSource"):
+        from . import inputs
+        return getattr(inputs, name)
+    raise AttributeError(name)
+
+
+__all__ = ["pydisort", "subroutines", "HenyeyGreenstein", "LevelSource"]

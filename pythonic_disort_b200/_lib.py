@@ -41,7 +41,8 @@ CHK = dict(TAU_POS=1 << 0, THICK_POS=1 << 1, OMEGA_RANGE=1 << 2, LEG_RANGE=1 << 
            MU0_AT_NODE=1 << 11)
 
 EXPORTS = ["pd_abi_version", "pd_workspace_bytes", "pd_prologue", "pd_solve", "pd_solve_stages", "pd_eval_flux", "pd_eval_u0",
-           "pd_eval_u", "pd_interp_mu", "pd_planck_band", "pd_s_poly_coeffs", "pd_hapke_modes", "pd_fp64_probe"]
+           "pd_eval_u", "pd_interp_mu", "pd_planck_band", "pd_s_poly_coeffs", "pd_hg_moments", "pd_level_source", "pd_hapke_modes",
+           "pd_fp64_probe"]
 
 
 def needs_build():
@@ -103,6 +104,10 @@ def bind(path):
     lib.pd_planck_band.argtypes = [ctypes.c_long, vp, ctypes.c_double, ctypes.c_double, vp, vp, vp]
     lib.pd_s_poly_coeffs.restype = ci
     lib.pd_s_poly_coeffs.argtypes = [ci, ci, vp, vp, ctypes.c_double, ctypes.c_double, vp, vp, vp]
+    lib.pd_hg_moments.restype = ci
+    lib.pd_hg_moments.argtypes = [ctypes.c_long, ci, vp, vp, vp]
+    lib.pd_level_source.restype = ci
+    lib.pd_level_source.argtypes = [ci, ci, vp, vp, vp, vp]
     lib.pd_hapke_modes.restype = ci
     lib.pd_hapke_modes.argtypes = [ci, ctypes.c_long, ci, ci, vp, vp, vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, vp, vp]
     lib.pd_fp64_probe.restype = ctypes.c_double

@@ -382,6 +382,8 @@ def _bc_tensor(b, name, B, N, NF, batched, T, is_zero=None):
 
 # Which inputs of a batched call carry the leading column axis is decided from each argument's RANK (the unbatched
 # rank is fixed by the reference's signature), never from "shape[0] happens to equal B".
+from .inputs import DeviceInput, HenyeyGreenstein, LevelSource  # noqa: E402,F401
+
 POSITIONAL = ("tau_arr", "omega_arr", "NQuad", "Leg_coeffs_all", "mu0", "I0", "phi0")
 _UNBATCHED_NDIM = {"tau_arr": 1, "omega_arr": 1, "Leg_coeffs_all": 2, "f_arr": 1, "s_poly_coeffs": 2,
                    "mu0": 0, "I0": 0, "phi0": 0}
@@ -395,6 +397,8 @@ def carries_batch_axis(name, x, B, N=None, NF=None):
     """True if input `name` of a batched call (B columns) has the leading column axis."""
     if name == "BDRF_mode":
         return _is_array(x) and x.ndim == 1 and x.shape[0] == B
+    if isinstance(x, DeviceInput):
+        return x.batched(B)
     if not _is_array(x):
         return False
     if name in _UNBATCHED_NDIM:
@@ -517,7 +521,7 @@ def pydisort(
         raise NotImplementedError("autograd_compatible=True is not supported by the CUDA implementation.")
     lib, dev = _backend()
     ins = (tau_arr, omega_arr, Leg_coeffs_all, mu0, I0, phi0, b_pos, b_neg, f_arr, s_poly_coeffs)
-    want_torch = any(_is_dev_tensor(x) for x in ins)
+    want_torch = any(x.on_device() if isinstance(x, DeviceInput) else _is_dev_tensor(x) for x in ins)
 
     def T(x):
         if isinstance(x, torch.Tensor):
@@ -565,6 +569,8 @@ def pydisort(
 
     omega = per_layer(omega_arr, (), "The zeroth dimension of the shape of `omega_arr` does not match the number of "
                       "layers which is deduced from the length of `tau_arr`.")
+    if isinstance(Leg_coeffs_all, DeviceInput):  # described by a few numbers per layer: expanded by a kernel (inputs.py)
+        Leg_coeffs_all = Leg_coeffs_all.expand(lib, dev, T, tau)
     leg_in = T(Leg_coeffs_all)
     if leg_in.ndim == 1:
         leg_in = leg_in[None, :]
@@ -583,10 +589,12 @@ def pydisort(
     else:
         f = None
 
+    s_nonzero = hints["s_nonzero"] if "s_nonzero" in hints else _host_any_nonzero(s_poly_coeffs)
+    if isinstance(s_poly_coeffs, DeviceInput):
+        s_poly_coeffs = s_poly_coeffs.expand(lib, dev, T, tau)
     s_t = T(s_poly_coeffs)
     if s_t.ndim == 1:
         s_t = s_t[None, :]
-    s_nonzero = hints["s_nonzero"] if "s_nonzero" in hints else _host_any_nonzero(s_poly_coeffs)
     Ns = 0 if (s_t.numel() == 0 or not s_nonzero) else int(s_t.shape[-1])
     if Ns > 0:
         s_poly = per_layer(s_t, (None,), "The zeroth dimension of the shape of `s_poly_coeffs` does not match the "
@@ -726,6 +734,8 @@ def pydisort(
 
 def _host_any_nonzero(x):
     """Decide a structural flag from host data; a device tensor is never read back (-> "may be non-zero")."""
+    if isinstance(x, DeviceInput):
+        return any(_host_any_nonzero(p) for p in x.parts())
     if isinstance(x, torch.Tensor):
         if x.is_cuda:
             return x.numel() > 0

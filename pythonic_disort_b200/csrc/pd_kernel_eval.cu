@@ -338,6 +338,36 @@ __global__ void k_s_poly_coeffs(int L, const double* __restrict__ tau, const dou
     }
 }
 
+// Henyey-Greenstein moments g^k, k < NA: one thread per (layer, group of four moments), 256-bit stores.  pow() keeps
+// every moment within 2 ulp of the correctly rounded power (what numpy's g ** k gives); a running product would drift
+// by k / 2 ulp, which the NQuad = 32 problems amplify to 1e-11 of the radiances.
+__global__ void k_hg_moments(long n, int NA, const double* __restrict__ g, double* __restrict__ out) {
+    const int q4 = (NA + 3) / 4;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * q4) return;
+    const long i = idx / q4;
+    const int k0 = (int)(idx - i * q4) * 4;
+    const double gi = g[i];
+    double v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = (k0 + e == 0) ? 1.0 : ((k0 + e == 1) ? gi : pow(gi, (double)(k0 + e)));
+    double* o = out + i * NA + k0;
+    if ((NA & 3) == 0) pd_store4(o, v[0], v[1], v[2], v[3]);
+    else
+        for (int e = 0; e < 4 && k0 + e < NA; ++e) o[e] = v[e];
+}
+
+// thermal source linear in tau inside every layer, from its level values
+__global__ void k_level_source(long n, int L, const double* __restrict__ tau, const double* __restrict__ lev,
+                               double* __restrict__ s_poly) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const long b = idx / L;
+    const int l = (int)(idx - b * L);
+    const double x0 = (l == 0) ? 0.0 : tau[idx - 1], x1 = tau[idx];
+    pd_linear_segment(x0, lev[b * (L + 1) + l], x1, lev[b * (L + 1) + l + 1], s_poly + idx * 2);
+}
+
 // Hapke BDRF Fourier modes (row f4): one thread per (reflection node i, incidence cosine j); out[m][i][j]
 template <int NFMAX>
 __global__ void k_hapke_modes(int N, long M, int NF, int npanel, const double* __restrict__ gl, const double* __restrict__ mu,
@@ -363,6 +393,24 @@ int pd_hapke_modes(int N, long M, int NF, int npanel, const double* gl16, const 
     if (NF <= 16) k_hapke_modes<16><<<(unsigned)blocks, threads, 0, pd_stream(stream)>>>(N, M, NF, npanel, gl16, mu, mup, B0, HH, W, out);
     else if (NF <= 32) k_hapke_modes<32><<<(unsigned)blocks, threads, 0, pd_stream(stream)>>>(N, M, NF, npanel, gl16, mu, mup, B0, HH, W, out);
     else k_hapke_modes<64><<<(unsigned)blocks, threads, 0, pd_stream(stream)>>>(N, M, NF, npanel, gl16, mu, mup, B0, HH, W, out);
+    return (int)cudaGetLastError();
+}
+
+int pd_hg_moments(long n, int NLeg_all, const double* g, double* out, void* stream) {
+    if (n < 1 || NLeg_all < 1 || !g || !out) return -70;
+    const int threads = 256;
+    const long blocks = (n * ((NLeg_all + 3) / 4) + threads - 1) / threads;
+    if (blocks > 2147483647L) return -71;
+    k_hg_moments<<<(unsigned)blocks, threads, 0, pd_stream(stream)>>>(n, NLeg_all, g, out);
+    return (int)cudaGetLastError();
+}
+
+int pd_level_source(int B, int L, const double* tau, const double* lev, double* s_poly, void* stream) {
+    if (B < 1 || L < 1 || !tau || !lev || !s_poly) return -70;
+    const int threads = 256;
+    const long n = (long)B * L, blocks = (n + threads - 1) / threads;
+    if (blocks > 2147483647L) return -71;
+    k_level_source<<<(unsigned)blocks, threads, 0, pd_stream(stream)>>>(n, L, tau, lev, s_poly);
     return (int)cudaGetLastError();
 }
 

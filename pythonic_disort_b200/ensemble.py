@@ -170,6 +170,8 @@ def solve_ensemble(tau_arr, omega_arr, NQuad, Leg_coeffs_all, mu0, I0, phi0, *, 
     N = NQuad // 2
 
     def shared_to_device(name, x):
+        if isinstance(x, api.DeviceInput):
+            return x if x.batched(B) else x.with_parts(tuple(shared_to_device("", p) for p in x.parts()))
         if api._is_array(x) and not api.carries_batch_axis(name, x, B, N, NF) and not (isinstance(x, torch.Tensor) and x.is_cuda):
             return torch.as_tensor(np.asarray(x, dtype=np.float64) if isinstance(x, np.ndarray) else x, dtype=_F64).to(dev)
         return x
@@ -208,6 +210,8 @@ def solve_ensemble(tau_arr, omega_arr, NQuad, Leg_coeffs_all, mu0, I0, phi0, *, 
     moved = [0]
 
     def up(x):
+        if isinstance(x, api.DeviceInput):  # only the description crosses the link; pydisort() expands it on the device
+            return x.with_parts(tuple(up(p) for p in x.parts()))
         if isinstance(x, np.ndarray):
             x = torch.from_numpy(np.ascontiguousarray(x))
         if isinstance(x, torch.Tensor) and not x.is_cuda:

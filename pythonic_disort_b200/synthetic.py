@@ -11,6 +11,7 @@ from math import pi
 import numpy as np
 
 from . import subroutines as sub
+from .inputs import HenyeyGreenstein, LevelSource
 
 SEEDS = {"sw": 20260101, "lw": 20260102, "ha": 20260103}
 
@@ -57,7 +58,9 @@ def make(name, ncol, first=0):
     Returns a dict with batched positional arguments (``args``), batched keyword
     arguments (``kwargs``) for :func:`pythonic_disort_b200.pydisort`, the level
     grid ``tau_eval`` [B, L+1] and azimuths ``phi_eval`` on which the benchmark
-    evaluates, and ``outputs`` (which fields the workload asks for)."""
+    evaluates, and ``outputs`` (which fields the workload asks for).  ``compact`` (ensembles only): the inputs that
+    have a few-numbers-per-layer description (``inputs.HenyeyGreenstein`` / ``LevelSource``) in that form, to be passed
+    in place of the arrays of the same name."""
     if name == "sw":
         L, NQuad, NLeg_all = 60, 16, 32
         U = _uniform_block(SEEDS[name], first, ncol, 3 * L + 3)
@@ -77,7 +80,8 @@ def make(name, ncol, first=0):
                     args=(tau, omega, NQuad, Leg, mu0, pi / mu0, 0.0),
                     kwargs=dict(f_arr=Leg[:, :, NQuad].copy(), NT_cor=True, BDRF_Fourier_modes=[albedo]),
                     tau_eval=np.concatenate([np.zeros((ncol, 1)), tau], axis=1),
-                    phi_eval=np.array([0.0, pi / 2, pi]), outputs=("flux", "u"))
+                    phi_eval=np.array([0.0, pi / 2, pi]), outputs=("flux", "u"),
+                    compact=dict(Leg_coeffs_all=HenyeyGreenstein(g, NLeg_all)))
     if name == "lw":
         L, NQuad = 60, 8
         U = _uniform_block(SEEDS[name], first, ncol, 4 * L + 1)
@@ -93,7 +97,8 @@ def make(name, ncol, first=0):
                     args=(tau, omega, NQuad, Leg, np.zeros(ncol), np.zeros(ncol), 0.0),
                     kwargs=dict(only_flux=True, s_poly_coeffs=s_poly, b_pos=0.98 * planck[:, -1:],
                                 BDRF_Fourier_modes=[0.02]),
-                    tau_eval=lev, phi_eval=None, outputs=("flux",))
+                    tau_eval=lev, phi_eval=None, outputs=("flux",),
+                    compact=dict(Leg_coeffs_all=HenyeyGreenstein(g, NQuad + 1), s_poly_coeffs=LevelSource(planck)))
     if name == "ha":
         L, NQuad = 100, 32
         U = _uniform_block(SEEDS[name], first, ncol, 3 * L)
@@ -108,7 +113,8 @@ def make(name, ncol, first=0):
                     kwargs=dict(BDRF_Fourier_modes=modes),
                     tau_eval=np.concatenate([np.zeros((ncol, 1)), tau], axis=1),
                     phi_eval=np.linspace(0, pi, 5), outputs=("flux", "u"),
-                    mu_user=np.array([-0.9, -0.5, -0.1, 0.1, 0.5, 0.9]))
+                    mu_user=np.array([-0.9, -0.5, -0.1, 0.1, 0.5, 0.9]),
+                    compact=dict(Leg_coeffs_all=HenyeyGreenstein(g, NQuad + 1)))
     if name in ("tp9c16", "tp9c"):
         # DISORT test problem 9c (pydisotest/9_test.py:175-236); "16" = the NQuad=16 variant
         NQuad = 16 if name == "tp9c16" else 8

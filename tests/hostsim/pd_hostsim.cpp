@@ -254,6 +254,21 @@ int pd_interp_mu(int B, int n2, long M, int nmu, const double* wts, const double
     return 0;
 }
 
+int pd_hg_moments(long n, int NA, const double* g, double* out, void*) {
+    for (long i = 0; i < n; ++i) {
+        for (int k = 0; k < NA; ++k) out[i * NA + k] = (k == 0) ? 1.0 : ((k == 1) ? g[i] : pow(g[i], (double)k));
+    }
+    return 0;
+}
+
+int pd_level_source(int B, int L, const double* tau, const double* lev, double* s_poly, void*) {
+    for (long b = 0; b < B; ++b)
+        for (int l = 0; l < L; ++l)
+            pd_linear_segment(l == 0 ? 0.0 : tau[b * L + l - 1], lev[b * (L + 1) + l], tau[b * L + l], lev[b * (L + 1) + l + 1],
+                              s_poly + (b * L + l) * 2);
+    return 0;
+}
+
 int pd_planck_band(long n, const double* T, double wlo, double whi, const double* gl16, double* out, void*) {
     if (n < 1 || !T || !gl16 || !out) return -50;
     for (long i = 0; i < n; ++i) out[i] = pd_planck_band_value(T[i], wlo, whi, gl16);

@@ -5,7 +5,8 @@ import warnings
 import numpy as np
 
 import golden_io
-from pythonic_disort_b200 import synthetic
+from pythonic_disort_b200 import api, parallel, synthetic
+from pythonic_disort_b200 import ensemble as pd_ensemble
 from pythonic_disort_b200.subroutines import _compare
 
 
@@ -277,6 +278,52 @@ def check_interface_levels_vs_assembled(pydisort, name, ncol, first=0, typical=1
     for key in again:
         assert np.array_equal(again[key], with_table[0][key]), key
     return worst
+
+
+def with_compact(ens):
+    """(args, kwargs) of the ensemble with its compact input descriptions in place of the arrays."""
+    args, kw = list(ens["args"]), dict(ens["kwargs"])
+    for name, obj in ens["compact"].items():
+        if name in api.POSITIONAL:
+            args[api.POSITIONAL.index(name)] = obj
+        else:
+            kw[name] = obj
+    return tuple(args), kw
+
+
+def check_compact_inputs(pd, name, ncol, chunk, first=0):
+    """inputs.HenyeyGreenstein / LevelSource in place of Leg_coeffs_all / s_poly_coeffs: same results as the arrays
+    (to the rounding of the moments), through pydisort(), solve_ensemble() and the sharding rule; only the description
+    is uploaded."""
+    ens = synthetic.make(name, ncol, first)
+    ref = run_batched(pd.pydisort, ens)
+    cargs, ckw = with_compact(ens)
+    got = run_batched(pd.pydisort, dict(ens, args=cargs, kwargs=ckw))
+    for key in ref:
+        # moments differ by an ulp between pow implementations; the NQuad = 32 columns answer that with 1.5e-11 of scale
+        np.testing.assert_allclose(got[key], ref[key], rtol=0, atol=1e-10 * np.max(np.abs(ref[key])))
+    outputs = ("flux_up", "flux_down", "u0") + (("u",) if "u" in ens["outputs"] else ())
+    res = pd_ensemble.solve_ensemble(*cargs, tau=ens["tau_eval"], phi=ens["phi_eval"], outputs=outputs, chunk=chunk, **ckw)
+    full = pd_ensemble.solve_ensemble(*ens["args"], tau=ens["tau_eval"], phi=ens["phi_eval"], outputs=outputs, chunk=chunk,
+                                   **ens["kwargs"])
+    for key in res:
+        np.testing.assert_array_equal(res[key], got[key])
+    assert res.h2d_bytes < 0.5 * full.h2d_bytes
+    a, k, (lo, hi) = parallel.shard_inputs(ncol, cargs, ckw, rank=1, world=2)
+    part = run_batched(pd.pydisort, dict(ens, args=a, kwargs=k, tau_eval=ens["tau_eval"][lo:hi]))
+    np.testing.assert_array_equal(part["flux_up"], got["flux_up"][lo:hi])
+    # one column, reference-style call
+    a1, k1 = synthetic.column_call(ens, 0)
+    a1, k1 = list(a1), dict(k1)
+    for nm, obj in ens["compact"].items():
+        if nm in api.POSITIONAL:
+            a1[api.POSITIONAL.index(nm)] = obj[0]
+        else:
+            k1[nm] = obj[0]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        one = pd.pydisort(*a1, **k1)
+    np.testing.assert_allclose(one[1](ens["tau_eval"][0]), got["flux_up"][0], rtol=1e-12)
 
 
 def check_actinic_vs_golden(pd_module, tol=1e-9):

@@ -37,6 +37,11 @@ def test_solve_ensemble_equals_the_batched_call(name, ncol, chunk):
     np.testing.assert_array_equal(again["flux_up"], ref["flux_up"])
 
 
+@pytest.mark.parametrize("name,ncol,chunk", [("sw", 4, 3), ("lw", 7, 3), ("ha", 2, 1)])
+def test_inputs_described_per_layer_and_expanded_on_the_device(name, ncol, chunk):
+    parity_suite.check_compact_inputs(pd, name, ncol, chunk)
+
+
 def test_solve_ensemble_at_user_polar_angles():
     ens = synthetic.make("ha", 2)
     with warnings.catch_warnings():

@@ -222,6 +222,13 @@ def test_interface_levels_come_from_the_sweep_and_agree_with_the_assembled_solut
     parity_suite.check_interface_levels_vs_assembled(pd.pydisort, name, ncol, first)
 
 
+@pytest.mark.parametrize("name,ncol,chunk", [("sw", 96, 40), ("lw", 1000, 300), ("ha", 6, 4)])
+def test_inputs_described_per_layer_and_expanded_on_the_device(name, ncol, chunk):
+    """inputs.HenyeyGreenstein / LevelSource (pd_hg_moments, pd_level_source) in place of the arrays: same results to the
+    rounding of the moments, through pydisort(), solve_ensemble() and the sharding rule."""
+    parity_suite.check_compact_inputs(pd, name, ncol, chunk, first=4000)
+
+
 def test_unphysical_phase_function_is_flagged_not_crashed():
     """Moments that make the reduced matrices indefinite: the symmetric path must hand the item to the general
     solver, which reports the non-positive k^2 (the reference returns NaN / complex garbage here)."""
