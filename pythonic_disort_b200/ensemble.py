@@ -206,7 +206,20 @@ def solve_ensemble(tau_arr, omega_arr, NQuad, Leg_coeffs_all, mu0, I0, phi0, *, 
         cur = h2d_stream = d2h_stream = _NoStream()
         on = lambda s_: contextlib.nullcontext()  # noqa: E731
         new_event = _NoStream
-    h2d_stream.wait_stream(cur)   # inputs prepared on the caller's stream (if any) are complete before we read them
+    # inputs a caller prepared ON THE DEVICE (on its current stream) must be complete before the copy stream slices them;
+    # host inputs need no such ordering, and without it the first upload of this call overlaps whatever the compute
+    # stream is still working on (the tail of the previous ensemble, when calls are issued back to back with wait=False)
+    def _on_device(x):
+        if isinstance(x, api.DeviceInput):
+            return x.on_device()
+        if isinstance(x, (list, tuple)):
+            return any(_on_device(y) for y in x)
+        if isinstance(x, api.TabulatedBDRF):
+            return False  # tables were placed on the device above, on the current stream, and are only read by kernels on it
+        return isinstance(x, torch.Tensor) and x.is_cuda and x.ndim > 0 and x.shape[0] == B
+
+    if any(_on_device(x) for x in list(args) + list(kwargs.values()) + [tau_q]):
+        h2d_stream.wait_stream(cur)
     moved = [0]
 
     def up(x):

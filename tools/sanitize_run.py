@@ -32,6 +32,20 @@ for name, ncol in (("sw", 6), ("lw", 20), ("ha", 2)):
         u = out[4](t, ens["phi_eval"])
         um = pd.subroutines.interpolate(out[4])(np.array([0.3, -0.3]), t, ens["phi_eval"])
         chk += float(np.sum(u)) + float(np.sum(um))
+    # levels between the interfaces: the output functions assemble G (C * exp) there instead of reading the sweep's
+    # interface radiances (a grid mixing both kinds sends some warps of k_eval_flux down each path)
+    tm = np.sort(np.concatenate([t, 0.5 * (t[:, :-1] + t[:, 1:])[:, ::2]], axis=1), axis=1)
+    chk += float(np.sum(out[1](tm))) + float(np.sum(out[3](tm)))
+    if "u" in ens["outputs"]:
+        chk += float(np.sum(out[4](tm, ens["phi_eval"])))
+    # the same ensemble described per layer (pd_hg_moments, pd_level_source)
+    args, kw = list(ens["args"]), dict(ens["kwargs"])
+    for nm, obj in ens["compact"].items():
+        if nm == "Leg_coeffs_all":
+            args[3] = obj
+        else:
+            kw[nm] = obj
+    chk += float(np.sum(pd.pydisort(*args, **kw)[1](t)))
     assert np.isfinite(chk), name
     print(name, "ok", chk)
 from pythonic_disort_b200 import _lib  # noqa: E402
