@@ -727,7 +727,10 @@ def pydisort(
 
     mu_arr = np.concatenate([mu_h, -mu_h])
     if want_torch:
-        mu_arr = torch.as_tensor(mu_arr, dtype=_F64, device=dev)
+        # from the cached device copy of the nodes: a fresh upload from pageable host memory would make the host wait
+        # for everything already queued on the stream (measured: the ensemble pipeline then runs in lock-step with
+        # the GPU, one chunk at a time)
+        mu_arr = torch.cat([mu_d, -mu_d])
     outs = _make_functions(sol)
     return (mu_arr,) + (outs[:3] if only_flux else outs)
 
