@@ -751,13 +751,22 @@ def _host_any_nonzero(x):
     return bool(np.any(a != 0))
 
 
-def _raise_for_pending(pending):
-    """Evaluate queued device-side checks with ONE device->host copy and raise / warn like the reference."""
+def _pending_flags(pending):
+    """One int64 per queued device-side check (its maximum), as ONE device tensor (enqueued on the current stream)."""
+    return torch.stack([f.reshape(-1).max().to(torch.int64) if f.numel() else torch.zeros((), dtype=torch.int64,
+                                                                                           device=f.device)
+                        for _, f in pending])
+
+
+def _raise_for_pending(pending, flat=None):
+    """Evaluate queued device-side checks with ONE device->host copy and raise / warn like the reference.  ``flat``:
+    the values of ``_pending_flags(pending)`` if the caller already has them on the host (the ensemble pipeline brings
+    them over on its download stream: reading them here would make the host wait for everything queued on the compute
+    stream, the next ensemble's chunks included)."""
     if not pending:
         return
-    flat = torch.stack([f.reshape(-1).max().to(torch.int64) if f.numel() else torch.zeros((), dtype=torch.int64,
-                                                                                           device=f.device)
-                        for _, f in pending]).cpu().tolist()
+    if flat is None:
+        flat = _pending_flags(pending).cpu().tolist()
     chk = bad = 0
     tau_range = False
     for (kind, f), v in zip(pending, flat):

@@ -79,6 +79,7 @@ class EnsembleResult(dict):
         super().__init__()
         self._done = None
         self._pending = []
+        self._flags = None   # host copy of the deferred checks' values (pinned; filled by the download stream)
         self.tensors = {}
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -89,8 +90,9 @@ class EnsembleResult(dict):
             self._done.synchronize()
             self._done = None
             pending, self._pending = self._pending, []
+            flags, self._flags = self._flags, None
             if pending:
-                api._raise_for_pending(pending)
+                api._raise_for_pending(pending, None if flags is None else flags.tolist())
         return self
 
 
@@ -280,6 +282,18 @@ def solve_ensemble(tau_arr, omega_arr, NQuad, Leg_coeffs_all, mu0, I0, phi0, *, 
             del sol, got
     res.h2d_bytes = moved[0]
     res.chunks = len(starts)
+    if res._pending:
+        # the values of the deferred checks travel with the results: reduced on the compute stream behind the last chunk,
+        # downloaded by the copy stream, read by wait() from host memory
+        flags = api._pending_flags(res._pending)
+        done = new_event()
+        done.record(cur)
+        res._flags = torch.empty(flags.shape, dtype=flags.dtype, pin_memory=cuda)
+        with on(d2h_stream):
+            d2h_stream.wait_event(done)
+            if cuda:
+                flags.record_stream(d2h_stream)
+            res._flags.copy_(flags, non_blocking=True)
     res._done = new_event()
     res._done.record(d2h_stream)
     return res.wait() if wait else res

@@ -18,6 +18,10 @@ name = sys.argv[1] if len(sys.argv) > 1 else "sw"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 8192
 ens = synthetic.make(name, B)
+if os.environ.get("PD_ONLY_FLUX"):   # the flux-only variant of a workload (bench.py: sw_flux)
+    ens["kwargs"]["only_flux"] = True
+    ens["kwargs"].pop("NT_cor", None)
+    ens["outputs"] = ("flux",)
 pin = lambda x: ensemble.pinned(x) if hasattr(x, "shape") and getattr(x, "ndim", 0) > 0 else x  # noqa: E731
 args = [pin(a) for a in ens["args"]]
 kw = {k: ([pin(m) for m in v] if k == "BDRF_Fourier_modes" else pin(v)) for k, v in ens["kwargs"].items()}
