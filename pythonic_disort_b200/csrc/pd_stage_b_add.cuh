@@ -239,8 +239,8 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
         }
     };
     // particular solution of layer l (hat basis) at the top (tau*_l, attenuation at) and bottom (tau*_{l+1}, ab)
-    auto particular = [&](int l, const double (&blp)[NJ], const double (&blm)[NJ], double at, double ab,
-                          double (&ptp)[NJ], double (&ptm)[NJ], double (&pbp)[NJ], double (&pbm)[NJ]) {
+    auto particular = [&](int l, double t_top, double t_bot, const double (&blp)[NJ], const double (&blm)[NJ], double at,
+                          double ab, double (&ptp)[NJ], double (&ptm)[NJ], double (&pbp)[NJ], double (&pbm)[NJ]) {
 #pragma unroll
         PD_FOR_OWN(ii, i) {
             double a = 0.0, c = 0.0, d = 0.0, e = 0.0;
@@ -252,10 +252,10 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
             }
             if (dthc) {
                 const double* dl = dthc + (long)l * A.Ns * N2;
-                a += pd_thermal_at(dl, A.Ns, N2, i, taus[l]);
-                c += pd_thermal_at(dl, A.Ns, N2, N + i, taus[l]);
-                d += pd_thermal_at(dl, A.Ns, N2, i, taus[l + 1]);
-                e += pd_thermal_at(dl, A.Ns, N2, N + i, taus[l + 1]);
+                a += pd_thermal_at(dl, A.Ns, N2, i, t_top);
+                c += pd_thermal_at(dl, A.Ns, N2, N + i, t_top);
+                d += pd_thermal_at(dl, A.Ns, N2, i, t_bot);
+                e += pd_thermal_at(dl, A.Ns, N2, N + i, t_bot);
             }
             ptp[ii] = Dj[ii] * a;
             ptm[ii] = Dj[ii] * c;
@@ -287,13 +287,17 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
     }
     stage_fwd(0);
     double att_t = 1.0;  // exp(-tau*_l / mu0), tau*_0 = 0
+    // the optical depths of the layer's two interfaces travel in registers, the next one is fetched a layer ahead (the
+    // dependent load at the top of every layer was a quarter of the kernel's global-memory stalls)
+    double t_top = taus[0], t_bot = taus[1];
     for (int l = 0; l < L; ++l) {
+        const double t_ahead = taus[(l + 2 <= L) ? l + 2 : L];
         stage_wait();
         const double* Gl = ring;
         const double* Kl = Gl + 2 * MAT;
         const double* Bl = Kl + N;
-        const double dtau = taus[l + 1] - taus[l];
-        const double att_b = beam ? exp(-taus[l + 1] * rmu0) : 0.0;
+        const double dtau = t_bot - t_top;
+        const double att_b = beam ? exp(-t_bot * rmu0) : 0.0;
 
         double Rh[NJ][N], Th[NJ][N], blp[NJ], blm[NJ];
         if (SPLIT) {
@@ -422,7 +426,7 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
         }
         // source terms
         double ptp[NJ], ptm[NJ], pbp[NJ], pbm[NJ];
-        particular(l, blp, blm, att_t, att_b, ptp, ptm, pbp, pbm);
+        particular(l, t_top, t_bot, blp, blm, att_t, att_b, ptp, ptm, pbp, pbm);
 #pragma unroll
         PD_FOR_OWN(ii, i) {
             vec[N + i] = ptm[ii];
@@ -484,6 +488,8 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
             }
         }
         att_t = att_b;
+        t_top = t_bot;
+        t_bot = t_ahead;
     }
     g.sync();
     if (SPLIT) stage(L - 1);  // the back sweep starts from the eigenvectors of the last layer
@@ -575,9 +581,12 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
     };
     load_history(L - 1);
     double att_b = att_t;  // exp(-tau*_L / mu0); the staging block holds (SPLIT: is being refilled with) layer L - 1
+    t_bot = taus[L];
+    t_top = taus[L - 1];
     for (int l = L - 1; l >= 0; --l) {
-        const double dtau = taus[l + 1] - taus[l];
-        const double at = beam ? exp(-taus[l] * rmu0) : 0.0;
+        const double t_ahead = taus[l > 0 ? l - 1 : 0];
+        const double dtau = t_bot - t_top;
+        const double at = beam ? exp(-t_top * rmu0) : 0.0;
 #pragma unroll
         PD_FOR_OWN(ii, i) vec[i] = ubp[ii];
         stage_wait();
@@ -603,7 +612,7 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
         g.sync();
         if (l > 0) stage(l - 1);
         double ptp[NJ], ptm[NJ], pbp[NJ], pbm[NJ];
-        particular(l, blp, blm, at, att_b, ptp, ptm, pbp, pbm);
+        particular(l, t_top, t_bot, blp, blm, at, att_b, ptp, ptm, pbp, pbm);
 #pragma unroll
         PD_FOR_OWN(ii, i) {
             const double htp = utp[ii] - ptp[ii], htm = utm[ii] - ptm[ii];
@@ -640,6 +649,8 @@ PD_HD bool pd_stage_b_add(const Grp& g, const PdStageB& A, int b, int m, double*
             ubm[ii] = utm[ii];
         }
         att_b = at;
+        t_bot = t_top;
+        t_top = t_ahead;
     }
     return !g.any(bad);
 }

@@ -79,7 +79,7 @@ PD_HD bool pd_stage_b_tps(const PdStageB& A, int b, int m, double* hist, long hs
         }
     };
     // particular solution of layer l (hat basis) at its top (attenuation at) and bottom (ab)
-    auto particular = [&](int l, double at, double ab, double (&ptp)[N], double (&ptm)[N], double (&pbp)[N],
+    auto particular = [&](int l, double t0, double t1, double at, double ab, double (&ptp)[N], double (&ptm)[N], double (&pbp)[N],
                           double (&pbm)[N]) {
         double top[N2], bot[N2];
 #pragma unroll
@@ -97,7 +97,6 @@ PD_HD bool pd_stage_b_tps(const PdStageB& A, int b, int m, double* hist, long hs
         }
         if (dthc) {
             const double* dl = dthc + (long)l * A.Ns * N2;
-            const double t0 = taus[l], t1 = taus[l + 1];
             if (A.Ns == 2) {  // source linear in tau (the usual case): both coefficient vectors with vector loads
 #pragma unroll
                 for (int i = 0; i < N2; i += 2) {
@@ -146,10 +145,12 @@ PD_HD bool pd_stage_b_tps(const PdStageB& A, int b, int m, double* hist, long hs
         S[i] = D[i] * (have_b ? bneg[i] : 0.0);
     }
     double att_t = 1.0;  // exp(-tau*_l / mu0), tau*_0 = 0
+    double t_top = taus[0], t_bot = taus[1];  // optical depths of the layer's interfaces; the next one is loaded a layer ahead
     for (int l = 0; l < L; ++l) {
         if (l + 1 < L) prefetch_layer(l + 1);
-        const double dtau = taus[l + 1] - taus[l];
-        const double att_b = beam ? exp(-taus[l + 1] * rmu0) : 0.0;
+        const double t_ahead = taus[(l + 2 <= L) ? l + 2 : L];
+        const double dtau = t_bot - t_top;
+        const double att_b = beam ? exp(-t_bot * rmu0) : 0.0;
         double R[N][N], T[N][N];
         {
             double V[N][N], U[N][N], dk[N];
@@ -195,7 +196,7 @@ PD_HD bool pd_stage_b_tps(const PdStageB& A, int b, int m, double* hist, long hs
                 }
         }
         double ptp[N], ptm[N], pbp[N], pbm[N];
-        particular(l, att_t, att_b, ptp, ptm, pbp, pbm);
+        particular(l, t_top, t_bot, att_t, att_b, ptp, ptm, pbp, pbm);
         double sminus[N], vq[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -286,6 +287,8 @@ PD_HD bool pd_stage_b_tps(const PdStageB& A, int b, int m, double* hist, long hs
             S[i] = s2;
         }
         att_t = att_b;
+        t_top = t_bot;
+        t_bot = t_ahead;
     }
 
     // ---------------------------------------------------------------- surface  (_solve_for_coeffs.py:121-134, :163, :248-254)
@@ -376,10 +379,13 @@ PD_HD bool pd_stage_b_tps(const PdStageB& A, int b, int m, double* hist, long hs
     };
     store_interface(L, ubp, ubm);
     double att_b = att_t;  // exp(-tau*_L / mu0)
+    t_bot = taus[L];
+    t_top = taus[L - 1];
     for (int l = L - 1; l >= 0; --l) {
         if (l > 0) prefetch_layer(l - 1);
-        const double dtau = taus[l + 1] - taus[l];
-        const double at = beam ? exp(-taus[l] * rmu0) : 0.0;
+        const double t_ahead = taus[l > 0 ? l - 1 : 0];
+        const double dtau = t_bot - t_top;
+        const double at = beam ? exp(-t_top * rmu0) : 0.0;
         const double* hl = hist + (long)l * F::HIST_PER_LAYER * hs;
         double utp[N], utm[N];
 #pragma unroll
@@ -397,7 +403,7 @@ PD_HD bool pd_stage_b_tps(const PdStageB& A, int b, int m, double* hist, long hs
         double V[N][N], U[N][N];
         eigvecs(l, V, U);
         double ptp[N], ptm[N], pbp[N], pbm[N];
-        particular(l, at, att_b, ptp, ptm, pbp, pbm);
+        particular(l, t_top, t_bot, at, att_b, ptp, ptm, pbp, pbm);
         double ps[N], ds[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -428,6 +434,8 @@ PD_HD bool pd_stage_b_tps(const PdStageB& A, int b, int m, double* hist, long hs
             ubm[i] = utm[i];
         }
         att_b = at;
+        t_bot = t_top;
+        t_top = t_ahead;
     }
     return !bad;
 }
