@@ -10,9 +10,13 @@ import warnings
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from pythonic_disort_b200 import api, ensemble, synthetic  # noqa: E402
+from pythonic_disort_b200 import api, ensemble, parallel, synthetic  # noqa: E402
 
 warnings.simplefilter("ignore")
+rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
+if world > 1:   # under torchrun: one rank per GPU, all ranks run the same pipeline at the same time (no communication)
+    parallel.bind_to_gpu_numa(local)
+torch.cuda.set_device(local)
 name = sys.argv[1] if len(sys.argv) > 1 else "sw"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 8192
@@ -62,7 +66,8 @@ for mode in ("one step, waited", "three steps back to back"):
     wall = e0.elapsed_time(e1)
     first = e0.elapsed_time(marks[0][1])
     last = marks[-1][1].elapsed_time(e1)
-    print(f"{mode}: wall {wall / n:.1f} ms per step; inside launches {sum(inside.values()) / n:.1f}; gaps between launches "
+    print(f"[rank {rank}] {mode}: wall {wall / n:.1f} ms per step; inside launches {sum(inside.values()) / n:.1f}; gaps between launches "
           f"{gaps / n:.1f}; before the first launch {first:.1f}; after the last launch (download tail) {last:.1f}; "
           f"host enqueue {host_ms / n:.1f} ms per step")
-    print("   ", {k: round(v / n, 1) for k, v in inside.items()})
+    if rank == 0:
+        print("   ", {k: round(v / n, 1) for k, v in inside.items()})
