@@ -29,6 +29,17 @@ def _worker(rank, world, port, out_dir):
         Fp = out[1](ens["tau_eval"][lo:hi])
     full = parallel.all_gather_columns(Fp, ens["B"])
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), full)
+    # the same shard through the one-call host pipeline, with the inputs that have a per-layer description passed as such
+    # (inputs.HenyeyGreenstein / LevelSource are cut like the arrays they stand for)
+    from pythonic_disort_b200 import ensemble
+    cargs, ckw = list(ens["args"]), dict(ens["kwargs"])
+    cargs[3] = ens["compact"]["Leg_coeffs_all"]
+    ckw["s_poly_coeffs"] = ens["compact"]["s_poly_coeffs"]
+    a2, k2, _ = parallel.shard_inputs(ens["B"], tuple(cargs), ckw)
+    with hostsim_backend.use(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = ensemble.solve_ensemble(*a2, tau=ens["tau_eval"][lo:hi], outputs=("flux_up",), chunk=4, **k2)
+    np.save(os.path.join(out_dir, f"compact{rank}.npy"), parallel.all_gather_columns(res["flux_up"], ens["B"]))
     dist.destroy_process_group()
 
 
@@ -50,3 +61,5 @@ def test_two_rank_sharded_solve_matches_single_process(tmp_path):
         got = np.load(os.path.join(str(tmp_path), f"rank{r}.npy"))
         assert got.shape == ref.shape
         np.testing.assert_array_equal(got, ref)
+        compact = np.load(os.path.join(str(tmp_path), f"compact{r}.npy"))
+        np.testing.assert_allclose(compact, ref, rtol=0, atol=1e-12 * np.max(np.abs(ref)))
